@@ -1,0 +1,181 @@
+/* mugiq_b200.h — C-ABI of the B200-native disconnected-loop hot path.
+ *
+ * Plain C, POD arguments only (raw device/host pointers, ints, doubles): this is the boundary a
+ * maintainer of ckallidonis/mugiq binds instead of the reference's CUDA translation units
+ * (lib/contract_wrappers.cu, lib/mugiq_{contract,displace,util}_kernels.cu) and the cuBLAS call in
+ * lib/loop_mugiq.cpp:358-387.  The reference itself has no true C ABI (MugiqLoopParam holds
+ * std::vector/std::string inside extern "C", include/mugiq.h:16-47); every entry point below cites
+ * the reference function it replaces.  INTEGRATION.md shows the reference-side call sites.
+ *
+ * Conventions
+ *  - Every function returns 0 on success and a negative MUGIQ_B200_E* code on failure;
+ *    mugiq_b200_last_error() returns a human-readable message for the calling thread.
+ *    (The reference aborts through errorQuda; the C++ mirror in mugiq_b200/host translates a
+ *    non-zero status into the same abort.)
+ *  - "_d" pointers are device pointers, "_h" pointers are host pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    asynchronous with respect to the host unless stated otherwise; nothing here calls
+ *    cudaDeviceSynchronize (the reference synchronises after every launch,
+ *    lib/contract_wrappers.cu:71,110,151,192).
+ *  - Complex numbers are interleaved (re, im) pairs of the field precision.
+ *
+ * Lattice geometry and memory layouts
+ *  - Sites use QUDA's even/odd (checkerboard) order: parity = (x+y+z+t)&1, x_cb = lexicographic>>1,
+ *    lexicographic = x + Lx*(y + Ly*(z + Lz*t));  full-site index x_eo = x_cb + parity*volumeCB
+ *    (this is `tid` of lib/mugiq_contract_kernels.cu:52).  L[0] must be even.
+ *  - Colour-spinor fields (12 complex per site, component index = colour + 3*spin,
+ *    include/util_mugiq.h:19):
+ *      MUGIQ_B200_ORDER_SITE   [parity][x_cb][spin][colour]           canonical, site-major (192 B/site FP64)
+ *      MUGIQ_B200_ORDER_FLOAT2 [parity][spin*3+colour][x_cb]          QUDA FLOAT2 native order
+ *      MUGIQ_B200_ORDER_FLOAT4 [parity][j=0..5][x_cb][2 complex]      QUDA FLOAT4 native order
+ *    All compute kernels consume the canonical site-major order; mugiq_b200_ingest_spinor /
+ *    mugiq_b200_export_spinor convert from/to the QUDA orders.
+ *  - Gauge field on the device: [mu][parity][x_cb][row][col] complex (the reference's host QDP order,
+ *    lib/displace.cpp:70-100, kept on the device), 144 B/link FP64.
+ *  - Position-space loop buffer ("dataPos"): complex index x_eo + V4*(G + 16*iL)
+ *    (lib/mugiq_contract_kernels.cu:120, lib/loop_mugiq.cpp:468,492).
+ *  - Momentum-projection input ("dataPosMP"): t + Lt*(G' + 16*iL) + Lt*nData*v3,
+ *    v3 = x + Lx*y + Lx*Ly*z  (lib/mugiq_util_kernels.cu:88-97).
+ *  - Momentum-space result ("dataMom"): t + Lt*(G' + 16*iL) + Lt*nData*im (lib/loop_mugiq.cpp:415-418).
+ */
+#ifndef MUGIQ_B200_H
+#define MUGIQ_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUGIQ_B200_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define MUGIQ_B200_OK 0
+#define MUGIQ_B200_EINVAL (-1)  /* bad argument (what errorQuda reports for bad params) */
+#define MUGIQ_B200_ECUDA (-2)   /* CUDA runtime error (what checkCudaError() reports) */
+#define MUGIQ_B200_ENOMEM (-3)  /* allocation failed */
+#define MUGIQ_B200_ESTATE (-4)  /* wrong call order */
+
+/* precision tags: numerically equal to QudaPrecision (4 = single, 8 = double) */
+#define MUGIQ_B200_PREC_SINGLE 4
+#define MUGIQ_B200_PREC_DOUBLE 8
+
+/* colour-spinor memory orders (see header comment) */
+#define MUGIQ_B200_ORDER_SITE 0
+#define MUGIQ_B200_ORDER_FLOAT2 2
+#define MUGIQ_B200_ORDER_FLOAT4 4
+
+/* displacement direction / sign: numerically equal to DisplaceDir / DisplaceSign (include/enum_mugiq.h:72-85) */
+#define MUGIQ_B200_DIR_X 0
+#define MUGIQ_B200_DIR_Y 1
+#define MUGIQ_B200_DIR_Z 2
+#define MUGIQ_B200_DIR_T 3
+#define MUGIQ_B200_SIGN_MINUS 0
+#define MUGIQ_B200_SIGN_PLUS 1
+
+#define MUGIQ_B200_NGAMMA 16
+#define MUGIQ_B200_MAX_ENTRIES 64 /* displacement entries per call of the fused path */
+
+/* Local lattice geometry.  Replaces ArgGeom (include/contract_util.cuh:71-120): dims, volumeCB and
+ * volume are derived from L; only full-site-subset fields are supported, as in the reference
+ * (lib/contract_wrappers.cu:100,185). */
+typedef struct mugiq_b200_geom_s {
+  int L[4];      /* local lattice extents x,y,z,t; L[0] even */
+  int precision; /* MUGIQ_B200_PREC_* of spinors, links and loop buffers */
+} mugiq_b200_geom_t;
+
+/* One displacement entry "<sign><dir>:<start>[,<stop>]" of the reference's --displace-entry-string
+ * (tests/loop.cpp:607-718; include/loop_mugiq.h:221-250). */
+typedef struct mugiq_b200_disp_entry_s {
+  int dir;   /* MUGIQ_B200_DIR_* */
+  int sign;  /* MUGIQ_B200_SIGN_* */
+  int start; /* first displacement length contracted (>= 1) */
+  int stop;  /* last displacement length contracted (>= start) */
+} mugiq_b200_disp_entry_t;
+
+/* ---- library -------------------------------------------------------------------------------- */
+int mugiq_b200_version(void);
+const char *mugiq_b200_last_error(void);
+/* Device query: fills name (<= name_len), SM count, compute capability major*10+minor, free and
+ * total device memory.  Replaces printGPUMemInfo (lib/util_mugiq.cpp:22-33). */
+int mugiq_b200_device_info(char *name, int name_len, int *sm_count, int *cc, long long *free_bytes,
+                           long long *total_bytes);
+
+/* ---- gamma tables ---------------------------------------------------------------------------- */
+/* Host copy of the tables the kernels have compiled in.  Replaces copyGammaCoeffStructToSymbol and
+ * copyGammaMapStructToSymbol (lib/contract_wrappers.cu:6-47; data include/gamma.h:32-109).
+ * row_value[16][4][2] (re,im), column_index[16][4], map_sign[16], map_index[16]; any pointer may be NULL. */
+int mugiq_b200_gamma_tables(double *row_value, int *column_index, double *map_sign, int *map_index);
+
+/* ---- layout conversion ----------------------------------------------------------------------- */
+/* QUDA FLOAT2/FLOAT4 -> canonical site-major and back (SURVEY §7 "layout contract"). */
+int mugiq_b200_ingest_spinor(void *dst_site_d, const void *src_d, int src_order,
+                             const mugiq_b200_geom_t *geom, void *stream);
+int mugiq_b200_export_spinor(void *dst_d, int dst_order, const void *src_site_d,
+                             const mugiq_b200_geom_t *geom, void *stream);
+/* Host QDP-order gauge (void* gauge[4], one pointer per direction, MugiqLoopParam::gauge,
+ * include/mugiq.h:43) -> device [mu][parity][x_cb][3][3].  Replaces Displace::createCudaGaugeField /
+ * createExtendedCudaGaugeField for an unpartitioned lattice (lib/displace.cpp:70-134).  Synchronous. */
+int mugiq_b200_gauge_upload(void *gauge_d, const void *const gauge_h[4], const mugiq_b200_geom_t *geom,
+                            void *stream);
+
+/* ---- stage 1: loop contraction --------------------------------------------------------------- */
+/* loop_d[x_eo + V4*G] += (1/sigma) * sum_{s2} rowval[G][s2] * sum_c conj(vL[s2,c]) * vR[col[G][s2],c]
+ * for the 16 G.  Replaces performLoopContraction (lib/contract_wrappers.cu:88-115) and
+ * loopContract_kernel (lib/mugiq_contract_kernels.cu:45-122); inv_sigma = 1.0/sigma as in
+ * LoopContractArg (include/contract_util.cuh:133). */
+int mugiq_b200_contract(void *loop_d, const void *vL_d, const void *vR_d, double sigma,
+                        const mugiq_b200_geom_t *geom, void *stream);
+/* Same sum for nvec eigenvector pairs in one launch with register accumulation and a single
+ * read-modify-write of loop_d (accumulate != 0) or a plain store (accumulate == 0).
+ * vL_d / vR_d are HOST arrays of nvec device pointers; vR_d == NULL means vR = vL (ultra-local). */
+int mugiq_b200_contract_batch(void *loop_d, const void *const *vL_d, const void *const *vR_d,
+                              const double *sigma_h, int nvec, int accumulate,
+                              const mugiq_b200_geom_t *geom, void *stream);
+
+/* ---- stage 2: covariant displacement ---------------------------------------------------------- */
+/* sign = PLUS : dst(x) = U_dir(x) * src(x + dir)
+ * sign = MINUS: dst(x) = U_dir(x - dir)^dagger * src(x - dir),  periodic wrap, dst != src.
+ * Replaces performCovariantDisplacementVector (lib/contract_wrappers.cu:171-198) and
+ * covariantDisplacementVector_kernel (lib/mugiq_displace_kernels.cu:156-185). */
+int mugiq_b200_displace(void *dst_d, const void *src_d, const void *gauge_d, int dir, int sign,
+                        const mugiq_b200_geom_t *geom, void *stream);
+
+/* ---- stages 1+2 fused: the eigenvector loop of Loop_Mugiq::computeCoarseLoop -------------------- */
+/* For every eigenvector n and every loop iL (0 = ultra-local, then the entries in order, lengths
+ * start..stop):  dataPos[x_eo + V4*(G + 16*iL)] (+)= (1/sigma_n) v_n(x)^dag Gamma_G (D^k v_n)(x).
+ * Replaces the body of the eigenvector/displacement loop nest lib/loop_mugiq.cpp:455-509 (including
+ * Displace::doVectorDisplacement, lib/displace.cpp:55-67) without materialising displaced vectors
+ * for one-hop entries.  evec_d is a HOST array of nvec device pointers (canonical order).
+ * workspace_d: device scratch of mugiq_b200_loop_workspace_bytes() bytes (may be NULL if that is 0).
+ * accumulate == 0 overwrites dataPos_d, != 0 adds to it (eigenvector batches / shards). */
+long long mugiq_b200_loop_workspace_bytes(const mugiq_b200_geom_t *geom, int nvec,
+                                          const mugiq_b200_disp_entry_t *entries, int nentries);
+int mugiq_b200_loop_accumulate(void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
+                               const void *gauge_d, const mugiq_b200_disp_entry_t *entries, int nentries,
+                               int accumulate, void *workspace_d, const mugiq_b200_geom_t *geom,
+                               void *stream);
+
+/* ---- stage 3: gamma-basis / time-slice reorder -------------------------------------------------- */
+/* out[t + Lt*((15-G) + 16*iL) + Lt*nData*v3] = sign[G] * in[x_eo + V4*(G + 16*iL)].
+ * Replaces convertIdxOrder_mapGamma (lib/contract_wrappers.cu:133-156,
+ * lib/mugiq_util_kernels.cu:59-99).  nData must equal 16*nLoop (lib/contract_wrappers.cu:138). */
+int mugiq_b200_reorder_mapgamma(void *out_d, const void *in_d, int nData, int nLoop,
+                                const mugiq_b200_geom_t *geom, void *stream);
+
+/* ---- stage 4: momentum projection --------------------------------------------------------------- */
+/* phase_d[v3 + V3*im] = cos(2 pi phi) + i*ftsign*sin(2 pi phi),
+ * phi = sum_d mom[d + 3*im]*(x_d + commCoord_d*localL_d)/totalL_d.
+ * Replaces createPhaseMatrixGPU (lib/contract_wrappers.cu:50-77, lib/mugiq_util_kernels.cu:3-35).
+ * mom_h: host int[3*Nmom] in MOM_MATRIX_IDX order (include/util_mugiq.h:24). */
+int mugiq_b200_phase_matrix(void *phase_d, const int *mom_h, int Nmom, int ftsign, const int localL[4],
+                            const int totalL[4], const int commCoord[4], int precision, void *stream);
+/* dataMom(M x N) = dataPosMP(M x K) * phase(K x N), all column-major, alpha = 1, beta = 0.
+ * Replaces cublasZgemm/cublasCgemm of lib/loop_mugiq.cpp:364-377.  workspace_d: device scratch of
+ * mugiq_b200_momproj_workspace_bytes(M, N, K, precision) bytes (split-K partial sums). */
+long long mugiq_b200_momproj_workspace_bytes(long long M, int N, long long K, int precision);
+int mugiq_b200_momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, int N,
+                       long long K, int precision, void *workspace_d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUGIQ_B200_H */

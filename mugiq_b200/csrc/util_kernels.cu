@@ -1,0 +1,197 @@
+// util_kernels.cu — stage 3 (gamma-basis / time-slice reorder), the phase matrix of stage 4, and the
+// QUDA-order <-> site-major layout conversion.
+//
+// Replaces /root/reference/lib/mugiq_util_kernels.cu:3-35 (phaseMatrix_kernel), :59-99
+// (convertIdxOrder_mapGamma_kernel) and their wrappers lib/contract_wrappers.cu:50-77,133-156.
+#include "kernels.cuh"
+
+namespace mugiq_b200 {
+
+// ---------------------------------------------------------------------------------------------------
+// Reorder:  out[t + Lt*((15-G) + 16*iL) + Lt*nData*v3] = sign[G] * in[x_eo + V4*(G + 16*iL)]
+//
+// The input is contiguous in x_eo for fixed (G,iL); the output is contiguous in t for fixed (G',iL,v3)
+// and then in idata.  A CTA owns kTileV (<= 16) spatial sites (consecutive v3) and all Lt time-slices for a chunk
+// of kTileD data columns: it gathers in[.] (coalesced along x within a lattice row) into a shared
+// [v3][idata][t] tile and writes runs of kTileD*Lt contiguous complex numbers per spatial site.
+// The reference writes each element with stride Lt*nData between neighbouring x
+// (lib/mugiq_util_kernels.cu:92-96).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTileD = 16;  // idata columns per CTA (one loop's 16 gammas)
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+reorder_mapgamma_kernel(F *__restrict__ out, const F *__restrict__ in, const int nLoop, const int kTileV,
+                        const LatGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cplx<F> *tile = reinterpret_cast<Cplx<F> *>(smem_raw);  // [kTileV][kTileD][Lt (+1 pad)]
+  constexpr GammaTables gt = gamma_tables();
+  const int Lt = g.L[3];
+  const int Ltp = Lt + 1;
+  const int nData = 16 * nLoop;
+  const int v3_0 = blockIdx.x * kTileV;
+  const int iL = blockIdx.y;
+
+  // gather: element e -> (G, t, dv) with dv fastest so that reads run along x
+  const int nElem = kTileD * Lt * kTileV;
+  for (int e = threadIdx.x; e < nElem; e += blockDim.x) {
+    const int dv = e % kTileV;
+    const int t = (e / kTileV) % Lt;
+    const int G = e / (kTileV * Lt);
+    const int v3 = v3_0 + dv;
+    if (v3 < g.V3) {
+      const int xx = v3 % g.L[0];
+      const int yz = v3 / g.L[0];
+      const int yy = yz % g.L[1];
+      const int zz = yz / g.L[1];
+      const int pty = (xx + yy + zz + t) & 1;
+      const int x_cb = (v3 + g.V3 * t) >> 1;
+      const size_t x_eo = (size_t)x_cb + (size_t)pty * g.volumeCB;
+      Cplx<F> z = ldg_c<F>(in + 2 * (x_eo + (size_t)g.volume * (G + 16 * iL)));
+      const F sgn = (F)gt.map_sign[G];
+      z.re *= sgn;
+      z.im *= sgn;
+      tile[(dv * kTileD + gt.map_index[G]) * Ltp + t] = z;
+    }
+  }
+  __syncthreads();
+  // scatter: for each spatial site a run of kTileD*Lt contiguous outputs
+  const int run = kTileD * Lt;
+  for (int e = threadIdx.x; e < run * kTileV; e += blockDim.x) {
+    const int r = e % run;
+    const int dv = e / run;
+    const int v3 = v3_0 + dv;
+    if (v3 < g.V3) {
+      const int t = r % Lt;
+      const int Gp = r / Lt;
+      const size_t o = (size_t)t + (size_t)Lt * (Gp + 16 * iL) + (size_t)Lt * nData * v3;
+      st_c<F>(out + 2 * o, tile[(dv * kTileD + Gp) * Ltp + t]);
+    }
+  }
+}
+
+int reorder_mapgamma(void *out_d, const void *in_d, int nLoop, const LatGeom &g, int precision, cudaStream_t stream) {
+  // spatial sites per CTA: as many as fit a ~96 KB tile, at most 16
+  const size_t per_site = (size_t)kTileD * (g.L[3] + 1) * 2 * prec_bytes(precision);
+  int kTileV = (int)((96 * 1024) / per_site);
+  if (kTileV > 16) kTileV = 16;
+  if (kTileV < 1) return set_error(MUGIQ_B200_EINVAL, "reorder_mapgamma: Lt=%d too large for the tile", g.L[3]);
+  const dim3 grid((g.V3 + kTileV - 1) / kTileV, nLoop);
+  const size_t smem = (size_t)kTileV * per_site;
+  if (precision == MUGIQ_B200_PREC_DOUBLE) {
+    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(reorder_mapgamma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    reorder_mapgamma_kernel<double><<<grid, 256, smem, stream>>>((double *)out_d, (const double *)in_d, nLoop, kTileV, g);
+  } else {
+    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(reorder_mapgamma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    reorder_mapgamma_kernel<float><<<grid, 256, smem, stream>>>((float *)out_d, (const float *)in_d, nLoop, kTileV, g);
+  }
+  MUGIQ_LAUNCH_CHECK();
+  return MUGIQ_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Phase matrix: phase[v3 + V3*im] = cos(2 pi phi) + i*sgn*sin(2 pi phi)   (lib/mugiq_util_kernels.cu:23-31)
+// phi is accumulated in double for both precisions and reduced with sincospi (exact argument
+// reduction), which agrees with the reference's cos(2.0*PI*phase) to a few ulp.
+// ---------------------------------------------------------------------------------------------------
+struct PhaseArg {
+  int localL[3], totalL[3], commCoord[3];
+  int V3, Nmom, ftsign;
+};
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+phase_matrix_kernel(F *__restrict__ phase, const int *__restrict__ mom, const PhaseArg a) {
+  const int v3 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (v3 >= a.V3) return;
+  const int a1 = v3 / a.localL[0];
+  const int a2 = a1 / a.localL[1];
+  const int gx = (v3 - a1 * a.localL[0]) + a.commCoord[0] * a.localL[0];
+  const int gy = (a1 - a2 * a.localL[1]) + a.commCoord[1] * a.localL[1];
+  const int gz = a2 + a.commCoord[2] * a.localL[2];
+  const double phi = (double)(mom[0 + 3 * im] * gx) / (double)a.totalL[0] +
+                     (double)(mom[1 + 3 * im] * gy) / (double)a.totalL[1] +
+                     (double)(mom[2 + 3 * im] * gz) / (double)a.totalL[2];
+  double s, c;
+  sincospi(2.0 * phi, &s, &c);
+  st_c<F>(phase + 2 * ((size_t)v3 + (size_t)a.V3 * im), make_c<F>((F)c, (F)((double)a.ftsign * s)));
+}
+
+// small persistent device buffer for the momentum table (avoids a cudaMalloc/cudaFree per call as in
+// lib/contract_wrappers.cu:54-76)
+int phase_matrix(void *phase_d, const int *mom_h, int Nmom, int ftsign, const int localL[4], const int totalL[4],
+                 const int commCoord[4], int precision, cudaStream_t stream) {
+  PhaseArg a;
+  a.V3 = 1;
+  for (int i = 0; i < 3; i++) {
+    a.localL[i] = localL[i];
+    a.totalL[i] = totalL[i];
+    a.commCoord[i] = commCoord ? commCoord[i] : 0;
+    a.V3 *= localL[i];
+  }
+  a.Nmom = Nmom;
+  a.ftsign = ftsign;
+  int *mom_d = nullptr;
+  MUGIQ_CUDA_CHECK(cudaMallocAsync((void **)&mom_d, sizeof(int) * 3 * Nmom, stream));
+  MUGIQ_CUDA_CHECK(cudaMemcpyAsync(mom_d, mom_h, sizeof(int) * 3 * Nmom, cudaMemcpyHostToDevice, stream));
+  const dim3 grid((a.V3 + 255) / 256, Nmom);
+  if (precision == MUGIQ_B200_PREC_DOUBLE)
+    phase_matrix_kernel<double><<<grid, 256, 0, stream>>>((double *)phase_d, mom_d, a);
+  else
+    phase_matrix_kernel<float><<<grid, 256, 0, stream>>>((float *)phase_d, mom_d, a);
+  MUGIQ_LAUNCH_CHECK();
+  MUGIQ_CUDA_CHECK(cudaFreeAsync(mom_d, stream));
+  // mom_h may be a temporary of the caller: make the copy complete before returning
+  MUGIQ_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return MUGIQ_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Layout conversion between QUDA's native colour-spinor orders and the canonical site-major order.
+// QUDA FloatNOrder<Float,4,3,N>: real element k = 2*(3*s+c)+reim of site x_cb lives at
+// parity_offset + ((k/N)*stride + x_cb)*N + k%N with stride = volumeCB (no pad), parity_offset =
+// parity*volumeCB*24.  One thread moves one complex number; reads are coalesced along x_cb in the QUDA
+// order and the site-major side is accessed with a 12-complex stride (served by L2 sectors).
+// ---------------------------------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256)
+convert_spinor_kernel(F *__restrict__ dst, const F *__restrict__ src, const int order, const int to_site,
+                      const LatGeom g) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (pty, comp, x_cb), x_cb fastest
+  const size_t total = (size_t)g.volume * kSpinorLen;
+  if (idx >= total) return;
+  const int x_cb = idx % g.volumeCB;
+  const int comp = (idx / g.volumeCB) % kSpinorLen;
+  const int pty = idx / ((size_t)g.volumeCB * kSpinorLen);
+  const size_t site_off = 2 * (((size_t)pty * g.volumeCB + x_cb) * kSpinorLen + comp);
+  size_t quda_off;
+  if (order == MUGIQ_B200_ORDER_FLOAT2) {
+    quda_off = (size_t)pty * g.volumeCB * 24 + 2 * ((size_t)comp * g.volumeCB + x_cb);
+  } else {  // FLOAT4: chunk j = comp/2 holds complex components 2j, 2j+1
+    quda_off = (size_t)pty * g.volumeCB * 24 + 4 * ((size_t)(comp >> 1) * g.volumeCB + x_cb) + 2 * (comp & 1);
+  }
+  if (to_site) {
+    dst[site_off] = src[quda_off];
+    dst[site_off + 1] = src[quda_off + 1];
+  } else {
+    dst[quda_off] = src[site_off];
+    dst[quda_off + 1] = src[site_off + 1];
+  }
+}
+
+int convert_spinor(void *dst_d, const void *src_d, int order, bool to_site, const LatGeom &g, int precision,
+                   cudaStream_t stream) {
+  const size_t total = (size_t)g.volume * kSpinorLen;
+  const int blocks = (int)((total + 255) / 256);
+  if (precision == MUGIQ_B200_PREC_DOUBLE)
+    convert_spinor_kernel<double><<<blocks, 256, 0, stream>>>((double *)dst_d, (const double *)src_d, order, to_site, g);
+  else
+    convert_spinor_kernel<float><<<blocks, 256, 0, stream>>>((float *)dst_d, (const float *)src_d, order, to_site, g);
+  MUGIQ_LAUNCH_CHECK();
+  return MUGIQ_B200_OK;
+}
+
+}  // namespace mugiq_b200

@@ -1,0 +1,269 @@
+"""Python mirror of the reference's operator interface for the hot path: `Loop_Mugiq`
+(/root/reference/include/loop_mugiq.h:12-136, lib/loop_mugiq.cpp) and `Displace`
+(include/displace.h:13-100, lib/displace.cpp).  Method names, argument meaning, buffer index orders and
+error behaviour follow the reference; all arithmetic happens in the CUDA library behind the C-ABI.
+
+What differs on purpose:
+  * the eigenvector x displacement loop nest is one C-ABI call per eigenvector batch instead of
+    4-6 synchronous launches and 3 field copies per eigenvector and hop;
+  * eigenvectors may be sharded over ranks (data-parallel over n); the loop buffer is then summed with one
+    NCCL allreduce instead of MPI_Reduce/Gather/Bcast on host buffers (lib/loop_mugiq.cpp:406-424);
+  * QUDA's eigensolver is an external input: `Eigsolve` only carries eVecs / eVals_sigma.
+"""
+import warnings
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import PREC_DOUBLE, PREC_SINGLE
+from .lattice import Lattice
+from .params import (MugiqLoopParam, LoopComputeParam, MugiqError, which_displace, DISPLACE_TYPE_COVARIANT,
+                     GAMMA_NAMES)
+
+
+class Eigsolve:
+    """Stands in for Eigsolve_Mugiq as far as the loop path reads it (include/eigsolve_mugiq.h): the
+    eigenvector fields `eVecs[n]` (device tensors [volume, 12] complex, canonical site-major even/odd order,
+    or HOST tensors when the loop streams them) and `eVals_sigma[n]` (host floats, sigma_n = sqrt(lambda_n),
+    lib/eigsolve_mugiq.cpp:289-315).  `L` are the local lattice extents the fields live on."""
+
+    def __init__(self, eVecs, eVals_sigma, L):
+        self.eVecs = list(eVecs)
+        self.eVals_sigma = [float(s) for s in eVals_sigma]
+        self.L = tuple(int(x) for x in L)
+        self.nEv = len(self.eVecs)
+        if self.nEv == 0:
+            raise MugiqError("Eigsolve: no eigenvectors")
+        if len(self.eVals_sigma) != self.nEv:
+            raise MugiqError("Eigsolve: eVals_sigma length does not match the number of eigenvectors")
+        vol = Lattice(self.L).volume
+        for v in self.eVecs:
+            if v.numel() != vol * 12 or not v.is_complex():
+                raise MugiqError("Eigsolve: eigenvectors must be complex fields of volume*12 elements "
+                                 "(full site subset, lib/contract_wrappers.cu:100)")
+
+    @property
+    def dtype(self):
+        return self.eVecs[0].dtype
+
+
+class Displace:
+    """Displace<F,order> (include/displace.h:13-100).  Owns the device gauge field and the auxiliary
+    displaced vector; the direction state machine is setupDisplacement -> doVectorDisplacement."""
+
+    def __init__(self, loopParams: MugiqLoopParam, L, dtype=torch.complex128, device="cuda"):
+        if loopParams.gauge is None:
+            raise MugiqError("Displace: loopParams.gauge is not set")
+        g0 = np.asarray(loopParams.gauge[0])
+        want = np.complex128 if dtype == torch.complex128 else np.complex64
+        # lib/displace.cpp:84-87: gauge precision must equal the template precision
+        if g0.dtype != want:
+            raise MugiqError(f"createCudaGaugeField: Incompatible precision settings between Displace template "
+                             f"{dtype} and gauge field parameters {g0.dtype}")
+        self.L = tuple(int(x) for x in L)
+        self.gaugeField = ops.gauge_upload(loopParams.gauge, self.L, device=device)
+        self.auxDispVec = torch.zeros((Lattice(self.L).volume, 12), dtype=dtype, device=device)
+        self.dispString = ""
+        self.dispDir = None
+        self.dispSign = None
+
+    def setupDisplacement(self, dStr: str):
+        self.dispString = dStr
+        self.dispDir, self.dispSign = which_displace(dStr)  # raises like WhichDisplaceFlag
+
+    def doVectorDisplacement(self, dispType, displacedEvec, idisp):
+        """One hop in place: displacedEvec <- U * shift(displacedEvec) (lib/displace.cpp:55-67).  The
+        reference's blas::zero + two field copies are replaced by a pointer swap of the storages."""
+        if dispType != DISPLACE_TYPE_COVARIANT:
+            raise MugiqError(f"Unsupported Displacement type {dispType}")
+        if self.dispDir is None:
+            raise MugiqError("doVectorDisplacement: setupDisplacement was not called")
+        ops.displace(self.auxDispVec, displacedEvec, self.gaugeField, self.dispDir, self.dispSign, self.L)
+        # swapAuxDispVec: exchange the underlying storages so the caller's tensor holds the result
+        tmp = displacedEvec.data
+        displacedEvec.data = self.auxDispVec.data
+        self.auxDispVec.data = tmp
+        return displacedEvec
+
+
+class Loop_Mugiq:
+    """Loop_Mugiq<Float,order> (include/loop_mugiq.h:12-136).
+
+    Buffers (same index orders as the reference):
+      dataPos_d  [nLoop, 16, V4]        x_eo + V4*(G + 16*iL)                   lib/loop_mugiq.cpp:468,492
+      dataPosMP_d[V3, nData, Lt]        t + Lt*idata + Lt*nData*v3              lib/mugiq_util_kernels.cu:88-97
+      dataMom_d  [Nmom, nData, Lt]      t + Lt*idata + Lt*nData*im              lib/loop_mugiq.cpp:415-418
+    `dataPos`, `dataMom` are the host copies; `dataMom_bcast` equals dataMom for a single time block.
+    `group` (optional torch.distributed process group): the eigenvectors given to this rank are its shard
+    of the full set; loop buffers are summed over the group after the local eigenvector loop.
+    """
+
+    def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64):
+        self.eigsolve = eigsolve_
+        self.group = group
+        self.evec_batch = int(evec_batch)
+        ev0 = eigsolve_.eVecs[0]
+        self.device = torch.device(device) if device is not None else (
+            ev0.device if ev0.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        self.dtype = eigsolve_.dtype
+        if self.dtype not in (torch.complex128, torch.complex64):
+            raise MugiqError("Loop_Mugiq: Precision not supported!")
+        self.precision = PREC_DOUBLE if self.dtype == torch.complex128 else PREC_SINGLE
+        self.L = eigsolve_.L
+        self.lat = Lattice(self.L)
+        self.cPrm = LoopComputeParam(loopParams_, self.L)
+        self.writeDataPos = bool(loopParams_.writePosSpaceHDF5)
+        self.writeDataMom = bool(loopParams_.writeMomSpaceHDF5)
+        self.momSpaceFilename = loopParams_.fname_mom_h5
+        self.posSpaceFilename = loopParams_.fname_pos_h5
+        self.MomProjDone = False
+        self.displace: Optional[Displace] = None
+        self.dataPos = self.dataMom = self.dataMom_h = self.dataMom_bcast = None
+        self.dataPosMP_d = self.dataMom_d = self.phaseMatrix_d = None
+        self._allocateDataMemory()
+        if self.cPrm.doMomProj:
+            self._createPhaseMatrix()
+        if self.cPrm.doNonLocal:
+            self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
+        self._workspace = None
+
+    # -- lib/loop_mugiq.cpp:102-158 ---------------------------------------------------------------------
+    def _allocateDataMemory(self):
+        p = self.cPrm
+        self.nElemPosLocPerLoop = p.nG * p.locV4
+        self.nElemPosLoc = self.nElemPosLocPerLoop * p.nLoop
+        self.nElemMomLoc = p.nG * p.Nmom * p.locT * p.nLoop
+        self.nElemMomTot = p.nG * p.Nmom * p.totT * p.nLoop
+        self.nElemPhMat = p.Nmom * p.locV3
+        self.dataPos_d = torch.zeros((p.nLoop, p.nG, p.locV4), dtype=self.dtype, device=self.device)
+        if p.doMomProj:
+            self.dataPosMP_d = torch.zeros((p.locV3, p.nData, p.locT), dtype=self.dtype, device=self.device)
+
+    def _createPhaseMatrix(self):
+        p = self.cPrm
+        mom = np.asarray(p.momMatrix, dtype=np.int32).reshape(p.Nmom, 3)
+        self.phaseMatrix_d = ops.phase_matrix(mom, p.FTSign, p.localL, p.totalL, (0, 0, 0, 0), dtype=self.dtype,
+                                              device=self.device)
+
+    # -- lib/loop_mugiq.cpp:440-525 ---------------------------------------------------------------------
+    def computeCoarseLoop(self):
+        p = self.cPrm
+        es = self.eigsolve
+        entries = p.entries() if p.doNonLocal else []
+        gauge = self.displace.gaugeField if self.displace is not None else None
+        need = ops.loop_workspace_bytes(self.L, self.precision, min(es.nEv, self.evec_batch), entries)
+        if need > 0 and (self._workspace is None or self._workspace.numel() < need):
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            if es.eVecs[0].is_cuda:
+                for b0 in range(0, es.nEv, self.evec_batch):
+                    b1 = min(es.nEv, b0 + self.evec_batch)
+                    ops.loop_accumulate(self.dataPos_d, es.eVecs[b0:b1], es.eVals_sigma[b0:b1], gauge, entries, self.L,
+                                        accumulate=b0 > 0, workspace=self._workspace)
+            else:
+                self._accumulate_from_host(entries, gauge)
+            if self.group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(torch.view_as_real(self.dataPos_d), op=dist.ReduceOp.SUM, group=self.group)
+            # "Always copy the device position-space buffer to the host" (lib/loop_mugiq.cpp:512)
+            if self.dataPos is None:
+                self.dataPos = torch.empty(self.dataPos_d.shape, dtype=self.dtype, pin_memory=True)
+            self.dataPos.copy_(self.dataPos_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if p.doMomProj:
+                self.performMomentumProjection()
+        return self
+
+    def _accumulate_from_host(self, entries, gauge):
+        """Eigenvectors resident in (pinned) HOST memory: double-buffered H2D copies of eigenvector batches on a
+        copy stream overlap the loop kernels of the previous batch."""
+        es = self.eigsolve
+        nb = max(1, min(self.evec_batch, es.nEv))
+        vol = self.lat.volume
+        stage = [torch.empty((nb, vol, 12), dtype=self.dtype, device=self.device) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        batches = [(b0, min(es.nEv, b0 + nb)) for b0 in range(0, es.nEv, nb)]
+
+        def issue(i):
+            b0, b1 = batches[i]
+            s = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(freed[s])
+                for k, n in enumerate(range(b0, b1)):
+                    stage[s][k].copy_(es.eVecs[n].reshape(vol, 12), non_blocking=True)
+                ready[s].record(copy_stream)
+
+        issue(0)
+        for i, (b0, b1) in enumerate(batches):
+            if i + 1 < len(batches):
+                issue(i + 1)
+            s = i & 1
+            main.wait_event(ready[s])
+            ops.loop_accumulate(self.dataPos_d, [stage[s][k] for k in range(b1 - b0)], es.eVals_sigma[b0:b1], gauge,
+                                entries, self.L, accumulate=i > 0, workspace=self._workspace)
+            freed[s].record(main)
+
+    # -- lib/loop_mugiq.cpp:323-434 ---------------------------------------------------------------------
+    def performMomentumProjection(self):
+        if self.MomProjDone:
+            raise MugiqError("performMomentumProjection: Not supposed to be called more than once!!")
+        p = self.cPrm
+        if p.nData != p.nLoop * 16:
+            raise MugiqError("performMomentumProjection: This function assumes that nData = nLoop * NGamma")
+        ops.reorder_mapgamma(self.dataPosMP_d, self.dataPos_d, p.nData, p.nLoop, self.L)
+        M, N, K = p.locT * p.nData, p.Nmom, p.locV3
+        self.dataMom_d = ops.momproj(self.dataPosMP_d, self.phaseMatrix_d, M, N, K).reshape(p.Nmom, p.nData, p.locT)
+        self.dataMom_h = self.dataMom_d.cpu()
+        # single spatial block and single time block: MPI_Reduce / MPI_Gather / MPI_Bcast are identities
+        self.dataMom = self.dataMom_h
+        self.dataMom_bcast = self.dataMom_h
+        self.MomProjDone = True
+
+    # -- result access in the reference's HDF5 naming (lib/loop_mugiq.cpp:582-633) -------------------------
+    def momentum_loops(self):
+        """{(mom tuple, disp tag, gamma name): complex array [T]} — the datasets writeLoopsHDF5_Mom creates."""
+        if not self.MomProjDone:
+            raise MugiqError("momentum_loops: momentum projection has not been performed")
+        p = self.cPrm
+        mom = np.asarray(p.momMatrix).reshape(p.Nmom, 3)
+        out = {}
+        data = self.dataMom.numpy()
+        for im in range(p.Nmom):
+            for iL, tag in enumerate(p.loop_tags()):
+                for ig in range(16):
+                    out[(tuple(int(x) for x in mom[im]), tag, GAMMA_NAMES[ig])] = data[im, ig + 16 * iL, :]
+        return out
+
+    def writeLoopsHDF5(self):
+        """Flag handling of lib/loop_mugiq.cpp:669-693; the file itself is written by mugiq_b200.h5lite."""
+        p = self.cPrm
+        if p.doMomProj:
+            if not self.writeDataMom:
+                warnings.warn("writeLoopsHDF5: Performed momentum projection, but got writeDatMom = FALSE. "
+                              "Will proceed to write momentum-space loop data")
+                self.writeDataMom = True
+            from .h5lite import write_momentum_loops
+            write_momentum_loops(self.momSpaceFilename, self)
+        elif not self.writeDataPos:
+            warnings.warn("writeLoopsHDF5: Did not perform momentum projection, but got writeDatPos = FALSE. "
+                          "Will proceed to write position-space loop data")
+            self.writeDataPos = True
+        if self.writeDataPos:
+            raise MugiqError("writeLoopsHDF5_Pos: Not supported yet!")  # lib/loop_mugiq.cpp:661-663
+
+
+def computeLoop(loopParams: MugiqLoopParam, eigsolve: Eigsolve, **kw):
+    """computeLoop<Float,order>(MugiqLoopParam, Eigsolve_Mugiq*) (lib/interface_mugiq.cpp:158-172)."""
+    loop = Loop_Mugiq(loopParams, eigsolve, **kw)
+    loop.computeCoarseLoop()
+    if loopParams.writeMomSpaceHDF5 or loopParams.writePosSpaceHDF5:
+        loop.writeLoopsHDF5()
+    else:
+        warnings.warn("computeLoop: Will NOT write output data!")
+    return loop

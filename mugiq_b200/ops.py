@@ -1,0 +1,179 @@
+"""Thin torch-tensor front end of the C-ABI (include/mugiq_b200.h): one function per entry point, same
+names and argument meaning.  Tensors only carry device memory and the current CUDA stream; every function
+checks that its operands live on a CUDA device and raises otherwise (no CPU path)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, make_geom, ptr_array, entry_array, PREC_DOUBLE, PREC_SINGLE
+
+
+def _prec(t):
+    if t.dtype in (torch.complex128, torch.float64):
+        return PREC_DOUBLE
+    if t.dtype in (torch.complex64, torch.float32):
+        return PREC_SINGLE
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _dev(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mugiq_b200 operates on CUDA tensors only (no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("mugiq_b200 needs contiguous tensors")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _volume(L):
+    return int(L[0]) * int(L[1]) * int(L[2]) * int(L[3])
+
+
+def gamma_tables():
+    rv = np.zeros((16, 4, 2), dtype=np.float64)
+    ci = np.zeros((16, 4), dtype=np.int32)
+    ms = np.zeros(16, dtype=np.float64)
+    mi = np.zeros(16, dtype=np.int32)
+    check(_lib.load().mugiq_b200_gamma_tables(rv.ctypes.data_as(_lib._pd), ci.ctypes.data_as(_lib._pi),
+                                              ms.ctypes.data_as(_lib._pd), mi.ctypes.data_as(_lib._pi)))
+    return rv, ci, ms, mi
+
+
+def device_info():
+    name = C.create_string_buffer(128)
+    sm, cc = C.c_int(), C.c_int()
+    fr, tot = C.c_longlong(), C.c_longlong()
+    check(_lib.load().mugiq_b200_device_info(name, 128, C.byref(sm), C.byref(cc), C.byref(fr), C.byref(tot)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": cc.value, "free": fr.value, "total": tot.value}
+
+
+def gauge_upload(gauge_h, L, device="cuda"):
+    """gauge_h: four host arrays (QDP order, one per direction) or one [4, volume, 3, 3] array."""
+    dirs = [np.ascontiguousarray(gauge_h[mu]) for mu in range(4)]
+    cdt = torch.complex128 if dirs[0].dtype == np.complex128 else torch.complex64
+    out = torch.empty((4, _volume(L), 3, 3), dtype=cdt, device=device)
+    geom = make_geom(L, _prec(out))
+    with torch.cuda.device(out.device):
+        check(_lib.load().mugiq_b200_gauge_upload(out.data_ptr(), ptr_array([d.ctypes.data for d in dirs]),
+                                                  C.byref(geom), _stream()))
+    return out
+
+
+def ingest_spinor(src, order, L):
+    _dev(src)
+    dst = torch.empty((_volume(L), 12), dtype=src.dtype, device=src.device)
+    geom = make_geom(L, _prec(src))
+    with torch.cuda.device(src.device):
+        check(_lib.load().mugiq_b200_ingest_spinor(dst.data_ptr(), src.data_ptr(), order, C.byref(geom), _stream()))
+    return dst
+
+
+def export_spinor(src_site, order, L):
+    _dev(src_site)
+    dst = torch.empty_like(src_site)
+    geom = make_geom(L, _prec(src_site))
+    with torch.cuda.device(src_site.device):
+        check(_lib.load().mugiq_b200_export_spinor(dst.data_ptr(), order, src_site.data_ptr(), C.byref(geom), _stream()))
+    return dst
+
+
+def contract(loop, vL, vR, sigma, L):
+    """performLoopContraction: loop += (1/sigma) * Tr[vL^dag Gamma vR]."""
+    _dev(loop, vL, vR)
+    geom = make_geom(L, _prec(vL))
+    with torch.cuda.device(vL.device):
+        check(_lib.load().mugiq_b200_contract(loop.data_ptr(), vL.data_ptr(), vR.data_ptr(), float(sigma),
+                                              C.byref(geom), _stream()))
+    return loop
+
+
+def contract_batch(loop, vLs, vRs, sigma, L, accumulate=True):
+    _dev(loop, *vLs)
+    if vRs is not None:
+        _dev(*vRs)
+    n = len(vLs)
+    sig = (C.c_double * max(n, 1))(*[float(s) for s in sigma])
+    geom = make_geom(L, _prec(loop))
+    with torch.cuda.device(loop.device):
+        check(_lib.load().mugiq_b200_contract_batch(
+            loop.data_ptr(), ptr_array([v.data_ptr() for v in vLs]),
+            ptr_array([v.data_ptr() for v in vRs]) if vRs is not None else None, sig, n, int(bool(accumulate)),
+            C.byref(geom), _stream()))
+    return loop
+
+
+def displace(dst, src, gauge, direction, sign, L):
+    """performCovariantDisplacementVector."""
+    _dev(dst, src, gauge)
+    geom = make_geom(L, _prec(src))
+    with torch.cuda.device(src.device):
+        check(_lib.load().mugiq_b200_displace(dst.data_ptr(), src.data_ptr(), gauge.data_ptr(), int(direction),
+                                              int(sign), C.byref(geom), _stream()))
+    return dst
+
+
+def loop_workspace_bytes(L, precision, nvec, entries):
+    geom = make_geom(L, precision)
+    return check(_lib.load().mugiq_b200_loop_workspace_bytes(C.byref(geom), nvec, entry_array(entries), len(entries)))
+
+
+def loop_accumulate(dataPos, evecs, sigma, gauge, entries, L, accumulate=False, workspace=None):
+    """The eigenvector/displacement loop nest of Loop_Mugiq::computeCoarseLoop for the given eigenvectors."""
+    _dev(dataPos, gauge, workspace, *evecs)
+    n = len(evecs)
+    prec = _prec(dataPos)
+    geom = make_geom(L, prec)
+    need = loop_workspace_bytes(L, prec, n, entries)
+    if need > 0 and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty(need, dtype=torch.uint8, device=dataPos.device)
+    sig = (C.c_double * n)(*[float(s) for s in sigma])
+    with torch.cuda.device(dataPos.device):
+        check(_lib.load().mugiq_b200_loop_accumulate(
+            dataPos.data_ptr(), ptr_array([v.data_ptr() for v in evecs]), sig, n,
+            gauge.data_ptr() if gauge is not None else None, entry_array(entries), len(entries),
+            int(bool(accumulate)), workspace.data_ptr() if workspace is not None else None, C.byref(geom), _stream()))
+    return dataPos
+
+
+def reorder_mapgamma(out, inp, nData, nLoop, L):
+    _dev(out, inp)
+    geom = make_geom(L, _prec(inp))
+    with torch.cuda.device(inp.device):
+        check(_lib.load().mugiq_b200_reorder_mapgamma(out.data_ptr(), inp.data_ptr(), int(nData), int(nLoop),
+                                                      C.byref(geom), _stream()))
+    return out
+
+
+def phase_matrix(mom, ftsign, localL, totalL=None, commCoord=(0, 0, 0, 0), dtype=torch.complex128, device="cuda"):
+    """mom: [Nmom][3] ints.  Returns phase[im, v3] (memory order v3 + V3*im)."""
+    mom = np.ascontiguousarray(np.asarray(mom, dtype=np.int32).reshape(-1, 3))
+    nmom = mom.shape[0]
+    totalL = totalL or localL
+    V3 = int(localL[0]) * int(localL[1]) * int(localL[2])
+    out = torch.empty((nmom, V3), dtype=dtype, device=device)
+    i4 = C.c_int * 4
+    with torch.cuda.device(out.device):
+        check(_lib.load().mugiq_b200_phase_matrix(out.data_ptr(), mom.ctypes.data_as(_lib._pi), nmom, int(ftsign),
+                                                  i4(*localL), i4(*totalL), i4(*commCoord), _prec(out), _stream()))
+    return out
+
+
+def momproj(posMP, phase, M, N, K, workspace=None):
+    """dataMom(M x N) = dataPosMP(M x K) * phase(K x N), column-major.  Returns a [N, M] tensor (memory m + M*n)."""
+    _dev(posMP, phase, workspace)
+    prec = _prec(posMP)
+    need = check(_lib.load().mugiq_b200_momproj_workspace_bytes(M, N, K, prec))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=posMP.device)
+    out = torch.empty((N, M), dtype=posMP.dtype, device=posMP.device)
+    with torch.cuda.device(posMP.device):
+        check(_lib.load().mugiq_b200_momproj(out.data_ptr(), posMP.data_ptr(), phase.data_ptr(), M, N, K, prec,
+                                             workspace.data_ptr(), _stream()))
+    return out

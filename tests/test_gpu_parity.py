@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+FP64 criterion: max|delta| / max|ref| <= 1e-12 (BASELINE.json north_star); FP32: 2e-5."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err, TOL_F64, TOL_F32
+from mugiq_b200 import synth, _lib
+from mugiq_b200.lattice import Lattice
+from mugiq_b200.params import MugiqLoopParam, momenta_up_to, MugiqError
+
+pytestmark = pytest.mark.gpu
+
+LATTICES = [(4, 4, 4, 8), (4, 2, 6, 4), (2, 2, 2, 2), (8, 4, 4, 6)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from mugiq_b200 import ops as o
+    info = o.device_info()
+    assert info["cc"] >= 100, f"expected an sm_100 device, got {info}"
+    return o
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def cdt(prec):
+    return np.complex128 if prec == 8 else np.complex64
+
+
+@pytest.mark.parametrize("L", LATTICES)
+@pytest.mark.parametrize("prec", [8, 4])
+def test_contract_single_pair(ops, oracle, L, prec):
+    """performLoopContraction: accumulating call, vL != vR and vL == vR."""
+    ev = synth.random_evecs_np(L, 2, seed=31).astype(cdt(prec))
+    V4 = ev.shape[1]
+    rng = np.random.default_rng(1)
+    init = (rng.standard_normal((16, V4)) + 1j * rng.standard_normal((16, V4))).astype(cdt(prec)) * 0.01
+    tol = TOL_F64 if prec == 8 else TOL_F32
+    for (a, b) in [(0, 1), (0, 0)]:
+        ref = oracle.contract(init.copy(), ev[a], ev[b], 0.37, L)
+        loop = dev(init)
+        vl, vr = dev(ev[a]), (dev(ev[b]) if b != a else None)
+        ops.contract(loop, vl, vr if vr is not None else vl, 0.37, L)
+        assert rel_err(host(loop), ref) < tol
+
+
+@pytest.mark.parametrize("L", LATTICES)
+@pytest.mark.parametrize("prec", [8, 4])
+def test_displace_all_directions(ops, oracle, L, prec):
+    v = synth.random_evecs_np(L, 1, seed=32)[0].astype(cdt(prec))
+    U = synth.random_gauge(L, seed=32).astype(cdt(prec))
+    gd = ops.gauge_upload(U, L)
+    vd = dev(v)
+    tol = 1e-14 if prec == 8 else 1e-6
+    for d in range(4):
+        for s in (0, 1):
+            out = torch.empty_like(vd)
+            ops.displace(out, vd, gd, d, s, L)
+            assert rel_err(host(out), oracle.displace(v, U, d, s, L)) < tol
+
+
+def test_contract_batch_accumulate_and_overwrite(ops, oracle):
+    L = (4, 4, 4, 8)
+    n = 7
+    ev = synth.random_evecs_np(L, n, seed=33)
+    ev2 = synth.random_evecs_np(L, n, seed=34)
+    sig = synth.sigmas(n)
+    V4 = ev.shape[1]
+    ref = np.zeros((16, V4), dtype=np.complex128)
+    for i in range(n):
+        oracle.contract(ref, ev[i], ev2[i], sig[i], L)
+    vl = [dev(ev[i]) for i in range(n)]
+    vr = [dev(ev2[i]) for i in range(n)]
+    loop = torch.full((16, V4), 7.0 + 1j, dtype=torch.complex128, device="cuda")
+    ops.contract_batch(loop, vl, vr, sig, L, accumulate=False)
+    assert rel_err(host(loop), ref) < TOL_F64
+    ops.contract_batch(loop, vl, vr, sig, L, accumulate=True)
+    assert rel_err(host(loop), 2 * ref) < TOL_F64
+    # ultra-local form (vR = NULL)
+    ref0 = np.zeros((16, V4), dtype=np.complex128)
+    for i in range(n):
+        oracle.contract(ref0, ev[i], ev[i], sig[i], L)
+    ops.contract_batch(loop, vl, None, sig, L, accumulate=False)
+    assert rel_err(host(loop), ref0) < TOL_F64
+    # empty batch: overwrite -> zeros, accumulate -> untouched
+    ops.contract_batch(loop, [], None, [], L, accumulate=True)
+    assert rel_err(host(loop), ref0) < TOL_F64
+    ops.contract_batch(loop, [], None, [], L, accumulate=False)
+    assert float(loop.abs().max()) == 0.0
+
+
+ENTRY_SETS = {
+    "ultralocal": [],
+    "onehop8": [(0, 1, 1, 1), (0, 0, 1, 1), (1, 1, 1, 1), (1, 0, 1, 1), (2, 1, 1, 1), (2, 0, 1, 1), (3, 1, 1, 1), (3, 0, 1, 1)],
+    "ranges": [(2, 1, 1, 3), (0, 0, 2, 2), (3, 0, 1, 2), (1, 1, 2, 4)],
+    "plus_only": [(0, 1, 1, 1), (3, 1, 1, 2)],
+    "minus_only": [(1, 0, 1, 1), (2, 0, 1, 3)],
+    "repeated": [(0, 1, 1, 1), (0, 1, 1, 1), (0, 0, 1, 2), (0, 1, 2, 2)],
+}
+
+
+@pytest.mark.parametrize("L", LATTICES)
+@pytest.mark.parametrize("name", list(ENTRY_SETS))
+def test_loop_accumulate_matches_oracle(ops, oracle, L, name):
+    entries = ENTRY_SETS[name]
+    nEv = 5
+    ev = synth.random_evecs_np(L, nEv, seed=35)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=35)
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    gd = ops.gauge_upload(U, L)
+    evd = [dev(ev[i]) for i in range(nEv)]
+    out = torch.full(ref.shape, 3.0, dtype=torch.complex128, device="cuda")
+    ops.loop_accumulate(out, evd, sig, gd, entries, L, accumulate=False)
+    assert rel_err(host(out), ref) < TOL_F64
+    # split into two batches, second accumulating: same sum
+    out2 = torch.full(ref.shape, -1.0, dtype=torch.complex128, device="cuda")
+    ops.loop_accumulate(out2, evd[:2], sig[:2], gd, entries, L, accumulate=False)
+    ops.loop_accumulate(out2, evd[2:], sig[2:], gd, entries, L, accumulate=True)
+    assert rel_err(host(out2), ref) < TOL_F64
+
+
+def test_loop_accumulate_float(ops, oracle):
+    L = (4, 4, 4, 8)
+    entries = ENTRY_SETS["onehop8"] + [(3, 1, 2, 3)]
+    ev = synth.random_evecs_np(L, 6, seed=36)
+    sig = synth.sigmas(6)
+    U = synth.random_gauge(L, seed=36)
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    gd = ops.gauge_upload(U.astype(np.complex64), L)
+    evd = [dev(ev[i].astype(np.complex64)) for i in range(6)]
+    out = torch.zeros(ref.shape, dtype=torch.complex64, device="cuda")
+    ops.loop_accumulate(out, evd, sig, gd, entries, L)
+    assert rel_err(host(out), ref) < TOL_F32
+
+
+def test_golden_fixture_16_evecs(ops):
+    """BASELINE.json configs[0] (4^3x8, 16 eigenvectors) against the committed golden vectors."""
+    from test_golden import load_golden
+    z, L, entries, ev, sig, U = load_golden()
+    gd = ops.gauge_upload(U, L)
+    evd = [dev(ev[i]) for i in range(len(ev))]
+    nLoop = 1 + sum(b - a + 1 for (_, _, a, b) in entries)
+    out = torch.zeros((nLoop, 16, ev.shape[1]), dtype=torch.complex128, device="cuda")
+    ops.loop_accumulate(out, evd, sig, gd, entries, L)
+    h = host(out)
+    assert rel_err(h[:, :, ::37], z["dataPos_sample"]) < TOL_F64
+    assert rel_err(h.sum(axis=2), z["dataPos_sums"]) < TOL_F64
+    mp = torch.empty((L[0] * L[1] * L[2], 16 * nLoop, L[3]), dtype=torch.complex128, device="cuda")
+    ops.reorder_mapgamma(mp, out, 16 * nLoop, nLoop, L)
+    ph = ops.phase_matrix(z["mom"], int(z["ftsign"]), L)
+    dm = ops.momproj(mp, ph, L[3] * 16 * nLoop, len(z["mom"]), L[0] * L[1] * L[2])
+    assert rel_err(host(dm).reshape(z["dataMom"].shape), z["dataMom"]) < TOL_F64
+
+
+@pytest.mark.parametrize("L", [(4, 4, 4, 8), (4, 2, 6, 4), (8, 4, 4, 6)])
+@pytest.mark.parametrize("prec", [8, 4])
+def test_reorder_mapgamma(ops, oracle, L, prec):
+    nLoop = 3
+    V4 = Lattice(L).volume
+    rng = np.random.default_rng(2)
+    inp = (rng.standard_normal((nLoop, 16, V4)) + 1j * rng.standard_normal((nLoop, 16, V4))).astype(cdt(prec))
+    ref = oracle.reorder_mapgamma(inp, nLoop, L)
+    out = torch.zeros(ref.shape, dtype=torch.complex128 if prec == 8 else torch.complex64, device="cuda")
+    ops.reorder_mapgamma(out, dev(inp), 16 * nLoop, nLoop, L)
+    assert np.array_equal(host(out), ref)  # pure data movement and sign flips: bit-exact
+    with pytest.raises(_lib.MugiqB200Error, match="nData = nLoop"):
+        ops.reorder_mapgamma(out, dev(inp), 16 * nLoop + 1, nLoop, L)
+
+
+@pytest.mark.parametrize("prec", [8, 4])
+@pytest.mark.parametrize("ftsign", [-1, 1])
+def test_phase_matrix(ops, oracle, prec, ftsign):
+    L = (4, 6, 8, 4)
+    tot = (8, 6, 16, 4)
+    cc = (1, 0, 1, 0)
+    mom = momenta_up_to(4)
+    ref = oracle.phase_matrix(mom, ftsign, L, tot, cc, dtype=cdt(prec))
+    out = ops.phase_matrix(mom, ftsign, L, tot, cc, dtype=torch.complex128 if prec == 8 else torch.complex64)
+    assert np.abs(host(out) - ref).max() < (4e-15 if prec == 8 else 3e-7)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1, 64), (4608, 1, 4096), (96, 7, 128), (1000, 19, 333), (512, 33, 512),
+                                   (130, 40, 70), (8, 3, 5)])
+def test_momproj_f64(ops, oracle, M, N, K):
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((K, M)) + 1j * rng.standard_normal((K, M))   # memory m + M*k
+    B = rng.standard_normal((N, K)) + 1j * rng.standard_normal((N, K))   # memory k + K*n
+    ref = oracle.gemm(A, B, M, N, K)
+    out = ops.momproj(dev(A), dev(B), M, N, K)
+    assert rel_err(host(out), ref) < TOL_F64
+
+
+def test_momproj_f32(ops, oracle):
+    M, N, K = 384, 7, 256
+    rng = np.random.default_rng(4)
+    A = (rng.standard_normal((K, M)) + 1j * rng.standard_normal((K, M))).astype(np.complex64)
+    B = (rng.standard_normal((N, K)) + 1j * rng.standard_normal((N, K))).astype(np.complex64)
+    ref = oracle.gemm(A.astype(np.complex128), B.astype(np.complex128), M, N, K)
+    out = ops.momproj(dev(A), dev(B), M, N, K)
+    assert rel_err(host(out), ref) < TOL_F32
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("prec", [8, 4])
+def test_ingest_export_quda_orders(ops, order, prec):
+    L = (4, 2, 6, 4)
+    lat = Lattice(L)
+    v = synth.random_evecs_np(L, 1, seed=37)[0].astype(cdt(prec))  # site-major [V4,12]
+    s = v.reshape(2, lat.volumeCB, 12)
+    if order == 2:   # [parity][comp][x_cb]
+        q = np.ascontiguousarray(s.transpose(0, 2, 1))
+    else:            # [parity][j][x_cb][2]
+        q = np.ascontiguousarray(s.reshape(2, lat.volumeCB, 6, 2).transpose(0, 2, 1, 3))
+    got = ops.ingest_spinor(dev(q.reshape(-1, 12)), order, L)
+    assert np.array_equal(host(got), v)
+    back = ops.export_spinor(got, order, L)
+    assert np.array_equal(host(back).ravel(), q.ravel())
+
+
+def test_error_reporting(ops):
+    L = (4, 4, 4, 4)
+    V4 = 256
+    v = torch.zeros((V4, 12), dtype=torch.complex128, device="cuda")
+    g = torch.zeros((4, V4, 3, 3), dtype=torch.complex128, device="cuda")
+    with pytest.raises(_lib.MugiqB200Error, match="direction"):
+        ops.displace(torch.empty_like(v), v, g, 4, 1, L)
+    with pytest.raises(_lib.MugiqB200Error, match="differ"):
+        ops.displace(v, v, g, 0, 1, L)
+    with pytest.raises(_lib.MugiqB200Error, match="even"):
+        ops.displace(torch.empty_like(v), v, g, 0, 1, (3, 4, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.displace(torch.empty_like(v), v.cpu(), g, 0, 1, L)
+
+
+def test_loop_mugiq_end_to_end(ops, oracle, tmp_path):
+    """The Loop_Mugiq mirror: device-resident and host-streamed eigenvectors, momentum projection, output."""
+    from mugiq_b200.loop import Loop_Mugiq, Eigsolve, computeLoop
+    from oracle import numpy_check as npc
+    L = (4, 4, 4, 8)
+    nEv = 9
+    ev = synth.random_evecs_np(L, nEv, seed=38)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=38)
+    prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
+    prm.set_displacements("+x:1;-y:1,2;+t:2")
+    mom = momenta_up_to(1)
+    prm.set_momenta(mom)
+    prm.writeMomSpaceHDF5 = True
+    prm.fname_mom_h5 = str(tmp_path / "loops.npz")
+    entries = [(0, 1, 1, 1), (1, 0, 1, 2), (3, 1, 2, 2)]
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    ref_mom = npc.momentum_projection(ref, mom, -1, L)
+    for resident in (True, False):
+        vecs = [dev(ev[i]) if resident else torch.from_numpy(ev[i]).pin_memory() for i in range(nEv)]
+        loop = computeLoop(prm, Eigsolve(vecs, sig, L), evec_batch=4)
+        assert rel_err(loop.dataPos.numpy(), ref) < TOL_F64
+        assert rel_err(loop.dataMom.numpy(), ref_mom) < TOL_F64
+        with pytest.raises(MugiqError, match="more than once"):
+            loop.performMomentumProjection()
+    z = np.load(prm.fname_mom_h5)
+    key = "mom_+1_+0_+0/disp_-y_2/g5g4/loop"
+    im = mom.index([1, 0, 0])
+    assert np.allclose(z[key][:, 0] + 1j * z[key][:, 1], ref_mom[im, 7 + 16 * 3, :], rtol=0, atol=1e-12 * np.abs(ref_mom).max())
+
+
+def test_displace_mirror_state_machine(ops, oracle):
+    from mugiq_b200.loop import Displace
+    from mugiq_b200.params import DISPLACE_TYPE_COVARIANT
+    L = (4, 4, 4, 4)
+    U = synth.random_gauge(L, seed=39)
+    v = synth.random_evecs_np(L, 1, seed=39)[0]
+    d = Displace(MugiqLoopParam(gauge=[U[mu] for mu in range(4)]), L)
+    vd = dev(v)
+    with pytest.raises(MugiqError):
+        d.doVectorDisplacement(DISPLACE_TYPE_COVARIANT, vd, 1)
+    with pytest.raises(MugiqError, match="Cannot parse"):
+        d.setupDisplacement("+w")
+    d.setupDisplacement("-z")
+    d.doVectorDisplacement(DISPLACE_TYPE_COVARIANT, vd, 1)
+    d.doVectorDisplacement(DISPLACE_TYPE_COVARIANT, vd, 2)
+    ref = oracle.displace(oracle.displace(v, U, 2, 0, L), U, 2, 0, L)
+    assert rel_err(host(vd), ref) < 1e-14
+    with pytest.raises(MugiqError, match="Unsupported Displacement"):
+        d.doVectorDisplacement(7, vd, 1)
+    with pytest.raises(MugiqError, match="Incompatible precision"):
+        Displace(MugiqLoopParam(gauge=[U[mu].astype(np.complex64) for mu in range(4)]), L)
+
+
+def test_full_size_properties(ops):
+    """BASELINE.json configs[1] lattice (16^3x32), a few eigenvectors: size-independent properties instead
+    of an oracle run — D_- D_+ = 1, linearity in the eigenvector set, minus loop = shifted dagger of plus loop,
+    p = 0 projection = spatial sum, sum_x T_1 = sum_n 1/sigma_n."""
+    L = (16, 16, 16, 32)
+    lat = Lattice(L)
+    nEv = 4
+    U = synth.random_gauge(L, seed=40)
+    gd = ops.gauge_upload(U, L)
+    ev = synth.random_evecs_torch(L, nEv, seed=40)
+    sig = synth.sigmas(nEv)
+    v = ev[0]
+    for d in range(4):
+        a, b = torch.empty_like(v), torch.empty_like(v)
+        ops.displace(a, v, gd, d, 1, L)
+        ops.displace(b, a, gd, d, 0, L)
+        assert float((b - v).abs().max() / v.abs().max()) < 1e-13
+    entries = [(0, 1, 1, 1), (0, 0, 1, 1), (3, 1, 1, 2), (3, 0, 1, 2)]
+    nLoop = 7
+    full = torch.zeros((nLoop, 16, lat.volume), dtype=torch.complex128, device="cuda")
+    ops.loop_accumulate(full, list(ev), sig, gd, entries, L)
+    parts = torch.zeros_like(full)
+    for n in range(nEv):
+        ops.loop_accumulate(parts, [ev[n]], sig[n:n + 1], gd, entries, L, accumulate=n > 0)
+    scale = float(full.abs().max())
+    assert float((full - parts).abs().max()) / scale < TOL_F64
+    assert abs(complex(full[0, 0].sum()) - (1.0 / sig).sum()) < 1e-10 * (1.0 / sig).sum()
+    # minus-x loop at x equals +-conj of the plus-x loop at x - mu (Gamma^dag = +-Gamma); same for t, 2 hops
+    from oracle import numpy_check as npc
+    g = npc.gamma_dense()
+    herm = torch.tensor([1.0 if np.allclose(g[G], g[G].conj().T) else -1.0 for G in range(16)], device="cuda")
+    for (d, k, ip, im_) in [(0, 1, 1, 2), (3, 1, 3, 5), (3, 2, 4, 6)]:
+        idx = np.arange(lat.volume)
+        for _ in range(k):
+            idx = lat.neighbour_eo(d, 0)[idx]
+        idx = torch.from_numpy(idx).cuda()
+        want = herm[:, None] * full[ip][:, idx].conj()
+        assert float((full[im_] - want).abs().max()) / scale < TOL_F64
+    # reorder + p=0 projection = signed spatial sum per time-slice
+    mp = torch.empty((lat.V3, 16 * nLoop, L[3]), dtype=torch.complex128, device="cuda")
+    ops.reorder_mapgamma(mp, full, 16 * nLoop, nLoop, L)
+    ph = ops.phase_matrix([[0, 0, 0]], -1, L)
+    dm = ops.momproj(mp, ph, L[3] * 16 * nLoop, 1, lat.V3).reshape(16 * nLoop, L[3])
+    ssum = mp.sum(dim=0)
+    assert float((dm - ssum).abs().max() / ssum.abs().max()) < TOL_F64
