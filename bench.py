@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the disconnected-loop hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One "step" = one pass of the whole hot path (stage 1 contraction over the 16 gammas + stage 2 covariant
+displacements + stage 3 gamma-map/time-slice reorder + stage 4 momentum projection) over the full eigenvector
+set of the workload.  Metric (BASELINE.json): eigvec·site contractions/s (16 gamma, all displacements)
+= nEv * V4 * nLoop / step time.  At N > 1 every rank holds its own shard of `nev` eigenvectors (weak scaling,
+gauge field replicated) and the step ends with the NCCL all-reduce of the loop buffer.
+
+Prints ONE JSON line on rank 0 (see the task contract): value (inputs resident in HBM), e2e (host buffers through
+the public Loop_Mugiq API, H2D/D2H inside the timed region), roofline of the dominant kernel measured live with
+CUDA events on the launching stream, cpu_baseline (the oracle port on the host cores, bounded sample), clocks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "eigvec_site_contractions_per_s"
+UNIT = "eigvec*site*loop contractions/s (16 gamma each)"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on; fits one GPU (5.0 GB of eigenvectors)
+    "16x16x16x32_nev200_ulocal+1hop8": dict(L=(16, 16, 16, 32), nev=200, entries="+x:1;-x:1;+y:1;-y:1;+z:1;-z:1;+t:1;-t:1",
+                                           p2max=1),
+    # BASELINE.json configs[2]
+    "24x24x24x48_nev500_disp1to4_p2le4": dict(L=(24, 24, 24, 48), nev=500,
+                                              entries="+x:1,4;-x:1,4;+y:1,4;-y:1,4;+z:1,4;-z:1,4;+t:1,4;-t:1,4", p2max=4),
+    # BASELINE.json configs[3], per-GPU share (1000 eigenvectors over 8 GPUs), ultra-local only
+    "32x32x32x64_nev125_ulocal": dict(L=(32, 32, 32, 64), nev=125, entries="", p2max=0),
+    # small case for quick checks
+    "8x8x8x16_nev16_ulocal+1hop8": dict(L=(8, 8, 8, 16), nev=16, entries="+x:1;-x:1;+y:1;-y:1;+z:1;-z:1;+t:1;-t:1", p2max=1),
+}
+DEFAULT_WORKLOAD = "16x16x16x32_nev200_ulocal+1hop8"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # NVML missing: report nulls
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_device_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            return local_rank
+    return local_rank
+
+
+def loop_count(entries):
+    return 1 + sum(b - a + 1 for (_, _, a, b) in entries)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (oracle/mugiq_oracle.cpp) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_loop_rate(wl, nev_sample, reps=1):
+    """Times the oracle's Loop_Mugiq::computeCoarseLoop restatement on `nev_sample` eigenvectors of the workload
+    (same lattice, same displacement entries), all host threads.  Returns (contractions/s, threads, seconds)."""
+    from oracle import oracle as orc
+    from mugiq_b200 import synth
+    from mugiq_b200.params import parse_disp_entries, which_displace
+    L = wl["L"]
+    entries = []
+    if wl["entries"]:
+        _, ds, a, b = parse_disp_entries(wl["entries"])
+        entries = [which_displace(s) + (x, y) for s, x, y in zip(ds, a, b)]
+    ev = synth.random_evecs_np(L, nev_sample, seed=5)
+    U = synth.random_gauge(L, seed=5) if entries else None
+    sig = synth.sigmas(nev_sample)
+    orc.compute_loop(ev[:1], sig[:1], U, entries[:1], L)  # warm-up (page faults, thread pool)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.compute_loop(ev, sig, U, entries, L)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    V4 = int(np.prod(L))
+    return nev_sample * V4 * loop_count(entries) / best, orc.num_threads(), best
+
+
+def cpu_sample_size(wl, target_s):
+    """Eigenvectors per CPU step so that one step costs about `target_s` seconds: calibrated with a 2-eigenvector
+    run on this host (the GPU box's core count differs from the build container's)."""
+    _, _, dt2 = cpu_loop_rate(wl, 2)
+    return int(max(2, min(wl["nev"], 2 * target_s / dt2)))
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nev_s = cpu_sample_size(wl, min(15.0, 150.0 / (args.steps + 1)))
+    times = []
+    rate = threads = None
+    for i in range(args.warmup + args.steps):
+        if i < args.warmup and i > 0:
+            continue  # one warm-up pass is enough for a CPU loop
+        r, threads, dt = cpu_loop_rate(wl, nev_s)
+        if i >= args.warmup:
+            times.append(dt)
+            rate = r if rate is None else max(rate, r)
+    V4 = int(np.prod(wl["L"]))
+    from mugiq_b200.params import parse_disp_entries
+    nloop = 1 + (sum(y - x + 1 for x, y in zip(*parse_disp_entries(wl["entries"])[2:])) if wl["entries"] else 0)
+    mean_dt = float(np.mean(times))
+    value = nev_s * V4 * nloop / mean_dt
+    sample = f"{nev_s} of {wl['nev']} eigenvectors per step, full lattice, all loops (oracle port, OpenMP)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": mean_dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "L": list(wl["L"]), "nev": wl["nev"], "entries": wl["entries"], "nLoop": nloop},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, wl, name):
+    import torch
+    import torch.distributed as dist
+    from mugiq_b200 import ops, synth
+    from mugiq_b200.loop import Loop_Mugiq, Eigsolve
+    from mugiq_b200.params import MugiqLoopParam, momenta_up_to
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    L, nev = wl["L"], args.nev or wl["nev"]
+    V4 = int(np.prod(L))
+    V3 = V4 // L[3]
+    U = synth.random_gauge(L, seed=11)
+    prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
+    if wl["entries"]:
+        prm.set_displacements(wl["entries"])
+    mom = momenta_up_to(wl["p2max"])
+    prm.set_momenta(mom)
+    sig = synth.sigmas(nev) + 0.2 * rank
+    ev_d = synth.random_evecs_torch(L, nev, seed=100 + rank, device=dev)          # [nev, V4, 12] resident in HBM
+    loop = Loop_Mugiq(prm, Eigsolve(list(ev_d), sig, L), device=dev, group=group, evec_batch=args.evec_batch,
+                      copy_pos_to_host=False)
+    nLoop = loop.cPrm.nLoop
+    units_per_rank = nev * V4 * nLoop
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ops.prof_reset()
+        ops.prof_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.__enter__()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        if sampler is not None:
+            sampler.__exit__()
+        ops.prof_enable(False)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    # ---- leg 1: inputs resident in HBM --------------------------------------------------------------------
+    def step_resident():
+        loop.MomProjDone = False
+        loop.computeCoarseLoop()
+
+    sampler = ClockSampler(physical_device_index(local_rank))
+    ms_step = timed(step_resident, args.steps, args.warmup, sampler)
+    report = ops.prof_report()
+    launches = sum(v["launches"] for v in report.values())
+    value = world * units_per_rank / (ms_step * 1e-3)
+
+    # dominant kernel and its roofline
+    peaks, peak_src = measured_peaks()
+    dom = max(report, key=lambda k: report[k]["ms"]) if report else None
+    roofline = None
+    if dom is not None and report[dom]["timed"] > 0:
+        d = report[dom]
+        per_launch_ms = d["ms"] / d["timed"]
+        per_launch_bytes = d["alg_bytes"] / d["launches"]
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(dom, {}).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                    "share_of_step": d["ms"] / (ms_step * args.steps),
+                    "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                                    "GBps": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
+                                for k, v in report.items()}}
+
+    # ---- leg 2: end to end through the public API with HOST buffers -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ev_h = torch.empty((nev, V4, 12), dtype=torch.complex128, pin_memory=True)
+        ev_h.copy_(ev_d)
+        del loop
+        loop_h = Loop_Mugiq(prm, Eigsolve(list(ev_h), sig, L), device=dev, group=group, evec_batch=args.evec_batch,
+                            copy_pos_to_host=True)
+
+        def step_host():
+            loop_h.MomProjDone = False
+            loop_h.displace.upload_gauge(prm) if loop_h.displace is not None else None   # H2D of the gauge field
+            loop_h.computeCoarseLoop()                                                    # H2D evecs, D2H dataPos + dataMom
+
+        e2e_steps = max(1, min(args.steps, 5))
+        ms_e2e = timed(step_host, e2e_steps, 1)
+        h2d = ev_h.numel() * 16 + (U.nbytes if loop_h.displace is not None else 0)
+        d2h = loop_h.dataPos.numel() * 16 + loop_h.dataMom.numel() * 16
+        e2e = {"value": world * units_per_rank / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "steps": e2e_steps}
+
+    # ---- cpu baseline (rank 0, N == 1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nev_s = cpu_sample_size(wl, 12.0)
+        rate, threads, dt = cpu_loop_rate(wl, nev_s)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{nev_s} of {nev} eigenvectors, full lattice, all {nLoop} loops, {dt:.1f} s (oracle port, OpenMP)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": name, "L": list(L), "nev_per_gpu": nev, "entries": wl["entries"], "nLoop": nLoop,
+                           "Nmom": len(mom), "stages": "contract+displace+reorder+momproj" + ("+allreduce" if world > 1 else ""),
+                           "l2": f"inputs larger than L2 ({nev * V4 * 192 / 1e9:.2f} GB of eigenvectors read per step)",
+                           "evec_batch": args.evec_batch},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--nev", type=int, default=0, help="override the eigenvector count per GPU (debugging)")
+    ap.add_argument("--evec-batch", type=int, default=200)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+    return run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

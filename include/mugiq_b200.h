@@ -175,6 +175,18 @@ long long mugiq_b200_momproj_workspace_bytes(long long M, int N, long long K, in
 int mugiq_b200_momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, int N,
                        long long K, int precision, void *workspace_d, void *stream);
 
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* Per-kernel launch counters (always on) and CUDA-event timers (while enabled) around every kernel launch
+ * of the library, recorded on the stream the kernel is launched on.  The reference only brackets
+ * init/total/free with QUDA TimeProfile (lib/interface_mugiq.cpp:36-47,193-244).  prof_query synchronises
+ * on the recorded events; alg_bytes_total is the ALGORITHMIC byte count of the timed launches. */
+int mugiq_b200_prof_enable(int on);
+int mugiq_b200_prof_reset(void);
+int mugiq_b200_prof_num_kernels(void);
+const char *mugiq_b200_prof_name(int kernel_id);
+int mugiq_b200_prof_query(int kernel_id, long long *launches, long long *timed_launches, double *ms_total,
+                          double *alg_bytes_total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,11 @@ SYMBOLS = {
     "mugiq_b200_phase_matrix": (_i, [_vp, _pi, _i, _i, _pi, _pi, _pi, _i, _vp]),
     "mugiq_b200_momproj_workspace_bytes": (_ll, [_ll, _i, _ll, _i]),
     "mugiq_b200_momproj": (_i, [_vp, _vp, _vp, _ll, _i, _ll, _i, _vp, _vp]),
+    "mugiq_b200_prof_enable": (_i, [_i]),
+    "mugiq_b200_prof_reset": (_i, []),
+    "mugiq_b200_prof_num_kernels": (_i, []),
+    "mugiq_b200_prof_name": (C.c_char_p, [_i]),
+    "mugiq_b200_prof_query": (_i, [_i, C.POINTER(_ll), C.POINTER(_ll), _pd, _pd]),
 }
 
 _lib = None

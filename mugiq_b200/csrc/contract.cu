@@ -73,6 +73,9 @@ static int launch_contract(void *loop_d, const VecBatch &batch, bool same, int a
                            cudaStream_t stream) {
   const int threads = 128;
   const int blocks = (g.volume + threads - 1) / threads;
+  // algorithmic bytes: S (ultra-local) or 2S per eigvec·site, accumulator written once (+ read if accumulating)
+  const double S = kSpinorLen * 2.0 * sizeof(F), A = 16 * 2.0 * sizeof(F);
+  ProfScope prof(K_CONTRACT, stream, (double)g.volume * (batch.nvec * (same ? S : 2 * S) + (accumulate ? 2 * A : A)));
   if (same)
     contract_batch_kernel<F, true><<<blocks, threads, 0, stream>>>((F *)loop_d, batch, accumulate, g);
   else

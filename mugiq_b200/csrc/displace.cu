@@ -79,6 +79,8 @@ int displace_batch(void *const *dst_d, const void *const *src_d, int nvec, const
       batch.src[i] = src_d[done + i];
       batch.dst[i] = dst_d[done + i];
     }
+    const double pb = (double)prec_bytes(precision);
+    ProfScope prof(K_DISPLACE, stream, (double)g.volume * pb * 2.0 * (batch.nvec * 2.0 * kSpinorLen + kLinkLen));
     if (precision == MUGIQ_B200_PREC_DOUBLE)
       displace_kernel<double><<<blocks, threads, 0, stream>>>(batch, (const double *)gauge_d, dir, sign, g);
     else

@@ -1,6 +1,7 @@
 // kernels.cuh — internal (C++) interface between the C-ABI layer (cabi.cu) and the per-stage kernels.
 #pragma once
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace mugiq_b200 {
 

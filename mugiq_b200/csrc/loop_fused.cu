@@ -52,7 +52,7 @@ int loop_accumulate(void *dataPos_d, const void *const *evec_d, const double *si
       for (int i = 0; i < nb; i++) src[i] = evec_d[b0 + i];
       int dispCount = 0;
       for (int k = 1; k <= en.stop; k++) {
-        for (int i = 0; i < nb; i++) dst[i] = static_cast<char *>(workspace_d) + ((size_t)(k & 1) * kLoopBatch + i) * fb;
+        for (int i = 0; i < nb; i++) dst[i] = static_cast<char *>(workspace_d) + ((size_t)(k & 1) * nb + i) * fb;
         rc = displace_batch(dst, src, nb, gauge_d, en.dir, en.sign, g, precision, stream);
         if (rc) return rc;
         for (int i = 0; i < nb; i++) src[i] = dst[i];

@@ -181,6 +181,9 @@ int momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, 
   long long kc;
   ksplit_for(M, N, K, precision, &ks, &kc);
   if (!workspace_d) return set_error(MUGIQ_B200_EINVAL, "momproj: workspace_d is NULL");
+  {
+  // algorithmic bytes: A once, phase once, result once; flops 8*M*N*K are reported by the caller
+  ProfScope prof(K_MOMPROJ, stream, 2.0 * prec_bytes(precision) * ((double)M * K + (double)K * N + (double)M * N));
   if (precision == MUGIQ_B200_PREC_DOUBLE && !use_simt()) {
     const int NT = nt_for(N);
     const dim3 grid((unsigned)((M + kRowsPerCta - 1) / kRowsPerCta), ks, (N + NT * 4 - 1) / (NT * 4));
@@ -206,8 +209,10 @@ int momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, 
                                                             (const float *)phase_d, M, N, K, kc);
     MUGIQ_LAUNCH_CHECK();
   }
+  }
   const long long nreal = 2 * M * N;
   const int blocks = (int)((nreal + 255) / 256);
+  ProfScope prof2(K_SPLITK_REDUCE, stream, (double)nreal * (ks + 1) * prec_bytes(precision));
   if (precision == MUGIQ_B200_PREC_DOUBLE)
     splitk_reduce_kernel<double><<<blocks, 256, 0, stream>>>((double *)mom_d, (const double *)workspace_d, nreal, ks);
   else

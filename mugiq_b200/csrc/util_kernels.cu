@@ -78,6 +78,7 @@ int reorder_mapgamma(void *out_d, const void *in_d, int nLoop, const LatGeom &g,
   if (kTileV < 1) return set_error(MUGIQ_B200_EINVAL, "reorder_mapgamma: Lt=%d too large for the tile", g.L[3]);
   const dim3 grid((g.V3 + kTileV - 1) / kTileV, nLoop);
   const size_t smem = (size_t)kTileV * per_site;
+  ProfScope prof(K_REORDER, stream, 2.0 * 16.0 * nLoop * (double)g.volume * 2.0 * prec_bytes(precision));
   if (precision == MUGIQ_B200_PREC_DOUBLE) {
     MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(reorder_mapgamma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
@@ -138,11 +139,14 @@ int phase_matrix(void *phase_d, const int *mom_h, int Nmom, int ftsign, const in
   MUGIQ_CUDA_CHECK(cudaMallocAsync((void **)&mom_d, sizeof(int) * 3 * Nmom, stream));
   MUGIQ_CUDA_CHECK(cudaMemcpyAsync(mom_d, mom_h, sizeof(int) * 3 * Nmom, cudaMemcpyHostToDevice, stream));
   const dim3 grid((a.V3 + 255) / 256, Nmom);
-  if (precision == MUGIQ_B200_PREC_DOUBLE)
-    phase_matrix_kernel<double><<<grid, 256, 0, stream>>>((double *)phase_d, mom_d, a);
-  else
-    phase_matrix_kernel<float><<<grid, 256, 0, stream>>>((float *)phase_d, mom_d, a);
-  MUGIQ_LAUNCH_CHECK();
+  {
+    ProfScope prof(K_PHASE, stream, (double)a.V3 * Nmom * 2.0 * prec_bytes(precision));
+    if (precision == MUGIQ_B200_PREC_DOUBLE)
+      phase_matrix_kernel<double><<<grid, 256, 0, stream>>>((double *)phase_d, mom_d, a);
+    else
+      phase_matrix_kernel<float><<<grid, 256, 0, stream>>>((float *)phase_d, mom_d, a);
+    MUGIQ_LAUNCH_CHECK();
+  }
   MUGIQ_CUDA_CHECK(cudaFreeAsync(mom_d, stream));
   // mom_h may be a temporary of the caller: make the copy complete before returning
   MUGIQ_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -186,6 +190,7 @@ int convert_spinor(void *dst_d, const void *src_d, int order, bool to_site, cons
                    cudaStream_t stream) {
   const size_t total = (size_t)g.volume * kSpinorLen;
   const int blocks = (int)((total + 255) / 256);
+  ProfScope prof(K_CONVERT, stream, 2.0 * (double)total * 2.0 * prec_bytes(precision));
   if (precision == MUGIQ_B200_PREC_DOUBLE)
     convert_spinor_kernel<double><<<blocks, 256, 0, stream>>>((double *)dst_d, (const double *)src_d, order, to_site, g);
   else

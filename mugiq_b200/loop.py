@@ -63,11 +63,21 @@ class Displace:
             raise MugiqError(f"createCudaGaugeField: Incompatible precision settings between Displace template "
                              f"{dtype} and gauge field parameters {g0.dtype}")
         self.L = tuple(int(x) for x in L)
-        self.gaugeField = ops.gauge_upload(loopParams.gauge, self.L, device=device)
+        self.device = device
+        self.gaugeField = None
+        self.upload_gauge(loopParams)
         self.auxDispVec = torch.zeros((Lattice(self.L).volume, 12), dtype=dtype, device=device)
         self.dispString = ""
         self.dispDir = None
         self.dispSign = None
+
+    def upload_gauge(self, loopParams: MugiqLoopParam):
+        """createCudaGaugeField (lib/displace.cpp:70-100): H2D copy of the host QDP-order links."""
+        if self.gaugeField is None:
+            self.gaugeField = ops.gauge_upload(loopParams.gauge, self.L, device=self.device)
+        else:
+            ops.gauge_upload(loopParams.gauge, self.L, device=self.device, out=self.gaugeField)
+        return self.gaugeField
 
     def setupDisplacement(self, dStr: str):
         self.dispString = dStr
@@ -100,10 +110,15 @@ class Loop_Mugiq:
     of the full set; loop buffers are summed over the group after the local eigenvector loop.
     """
 
-    def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64):
+    def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64,
+                 stream_batch=16, copy_pos_to_host=True):
         self.eigsolve = eigsolve_
         self.group = group
-        self.evec_batch = int(evec_batch)
+        self.evec_batch = int(evec_batch)      # eigenvectors per C-ABI call when they are device resident
+        self.stream_batch = int(stream_batch)  # eigenvectors per H2D staging buffer when they live on the host
+        # the reference always copies dataPos_d to the host (lib/loop_mugiq.cpp:512); a caller that only wants
+        # momentum-space data can switch the 16*V4*nLoop-complex D2H copy off
+        self.copy_pos_to_host = bool(copy_pos_to_host)
         ev0 = eigsolve_.eVecs[0]
         self.device = torch.device(device) if device is not None else (
             ev0.device if ev0.is_cuda else torch.device("cuda", torch.cuda.current_device()))
@@ -153,7 +168,8 @@ class Loop_Mugiq:
         es = self.eigsolve
         entries = p.entries() if p.doNonLocal else []
         gauge = self.displace.gaugeField if self.displace is not None else None
-        need = ops.loop_workspace_bytes(self.L, self.precision, min(es.nEv, self.evec_batch), entries)
+        nb_ws = self.evec_batch if es.eVecs[0].is_cuda else self.stream_batch
+        need = ops.loop_workspace_bytes(self.L, self.precision, min(es.nEv, nb_ws), entries)
         if need > 0 and (self._workspace is None or self._workspace.numel() < need):
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
@@ -164,14 +180,19 @@ class Loop_Mugiq:
                                         accumulate=b0 > 0, workspace=self._workspace)
             else:
                 self._accumulate_from_host(entries, gauge)
-            if self.group is not None:
+            # eigenvector shards: the position-space buffer is summed over the group only when it is
+            # needed on every rank (host copy requested or no momentum projection); otherwise the
+            # projection, which is linear, runs on the partial sums and the small dataMom is reduced
+            self._reduce_mom = self.group is not None and p.doMomProj and not self.copy_pos_to_host
+            if self.group is not None and not self._reduce_mom:
                 import torch.distributed as dist
                 dist.all_reduce(torch.view_as_real(self.dataPos_d), op=dist.ReduceOp.SUM, group=self.group)
             # "Always copy the device position-space buffer to the host" (lib/loop_mugiq.cpp:512)
-            if self.dataPos is None:
-                self.dataPos = torch.empty(self.dataPos_d.shape, dtype=self.dtype, pin_memory=True)
-            self.dataPos.copy_(self.dataPos_d, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            if self.copy_pos_to_host:
+                if self.dataPos is None:
+                    self.dataPos = torch.empty(self.dataPos_d.shape, dtype=self.dtype, pin_memory=True)
+                self.dataPos.copy_(self.dataPos_d, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
             if p.doMomProj:
                 self.performMomentumProjection()
         return self
@@ -180,7 +201,7 @@ class Loop_Mugiq:
         """Eigenvectors resident in (pinned) HOST memory: double-buffered H2D copies of eigenvector batches on a
         copy stream overlap the loop kernels of the previous batch."""
         es = self.eigsolve
-        nb = max(1, min(self.evec_batch, es.nEv))
+        nb = max(1, min(self.stream_batch, es.nEv))
         vol = self.lat.volume
         stage = [torch.empty((nb, vol, 12), dtype=self.dtype, device=self.device) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=self.device)
@@ -219,6 +240,9 @@ class Loop_Mugiq:
         ops.reorder_mapgamma(self.dataPosMP_d, self.dataPos_d, p.nData, p.nLoop, self.L)
         M, N, K = p.locT * p.nData, p.Nmom, p.locV3
         self.dataMom_d = ops.momproj(self.dataPosMP_d, self.phaseMatrix_d, M, N, K).reshape(p.Nmom, p.nData, p.locT)
+        if getattr(self, "_reduce_mom", False):
+            import torch.distributed as dist
+            dist.all_reduce(torch.view_as_real(self.dataMom_d), op=dist.ReduceOp.SUM, group=self.group)
         self.dataMom_h = self.dataMom_d.cpu()
         # single spatial block and single time block: MPI_Reduce / MPI_Gather / MPI_Bcast are identities
         self.dataMom = self.dataMom_h

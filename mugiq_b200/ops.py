@@ -54,11 +54,12 @@ def device_info():
     return {"name": name.value.decode(), "sm_count": sm.value, "cc": cc.value, "free": fr.value, "total": tot.value}
 
 
-def gauge_upload(gauge_h, L, device="cuda"):
+def gauge_upload(gauge_h, L, device="cuda", out=None):
     """gauge_h: four host arrays (QDP order, one per direction) or one [4, volume, 3, 3] array."""
     dirs = [np.ascontiguousarray(gauge_h[mu]) for mu in range(4)]
     cdt = torch.complex128 if dirs[0].dtype == np.complex128 else torch.complex64
-    out = torch.empty((4, _volume(L), 3, 3), dtype=cdt, device=device)
+    if out is None:
+        out = torch.empty((4, _volume(L), 3, 3), dtype=cdt, device=device)
     geom = make_geom(L, _prec(out))
     with torch.cuda.device(out.device):
         check(_lib.load().mugiq_b200_gauge_upload(out.data_ptr(), ptr_array([d.ctypes.data for d in dirs]),
@@ -176,4 +177,27 @@ def momproj(posMP, phase, M, N, K, workspace=None):
     with torch.cuda.device(posMP.device):
         check(_lib.load().mugiq_b200_momproj(out.data_ptr(), posMP.data_ptr(), phase.data_ptr(), M, N, K, prec,
                                              workspace.data_ptr(), _stream()))
+    return out
+
+
+# ---- instrumentation (mugiq_b200_prof_*) ---------------------------------------------------------------
+def prof_enable(on=True):
+    check(_lib.load().mugiq_b200_prof_enable(int(bool(on))))
+
+
+def prof_reset():
+    check(_lib.load().mugiq_b200_prof_reset())
+
+
+def prof_report():
+    """{kernel name: {"launches", "timed", "ms", "alg_bytes"}} for every kernel launched since the last reset."""
+    lib = _lib.load()
+    out = {}
+    for k in range(lib.mugiq_b200_prof_num_kernels()):
+        n, t = C.c_longlong(), C.c_longlong()
+        ms, b = C.c_double(), C.c_double()
+        check(lib.mugiq_b200_prof_query(k, C.byref(n), C.byref(t), C.byref(ms), C.byref(b)))
+        if n.value:
+            out[lib.mugiq_b200_prof_name(k).decode()] = {"launches": n.value, "timed": t.value, "ms": ms.value,
+                                                         "alg_bytes": b.value}
     return out
