@@ -154,6 +154,29 @@ int mugiq_b200_loop_accumulate(void *dataPos_d, const void *const *evec_d, const
                                int accumulate, void *workspace_d, const mugiq_b200_geom_t *geom,
                                void *stream);
 
+/* Plan form of the same loop nest, for callers that feed the eigenvectors in several batches (host-streamed
+ * batches, shards): the plan owns what depends on the gauge field and the entry list only — the Wilson lines
+ * W_k(x) = U(x) U(x+mu) ... U(x+(k-1)mu) (a displacement of length k is then ONE 3x3 multiply per site instead of
+ * k hops of lib/displace.cpp:55-67) and the launch schedule.  Plays the role of the Displace object
+ * (lib/displace.cpp:4-37) for the fused path.
+ *   create     : builds the Wilson lines on `stream` (allocates device memory for them)
+ *   accumulate : dataPos (+)= contribution of the given eigenvectors, for every loop the plan COMPUTES
+ *   finalize   : fills the slots the plan DERIVES after the eigenvector sum — the minus-direction loop of a
+ *                (+mu,-mu) entry pair from its plus partner, T-_G(x) = h_G conj(T+_G(x - k mu)) with
+ *                Gamma_G^dag = h_G Gamma_G (exact identity), and copies for repeated requests.  Call once, after
+ *                the last accumulate (and after any cross-rank reduction is fine too: it is linear).
+ * MUGIQ_B200_NO_PM_SYMMETRY=1 in the environment makes the plan compute every requested loop. */
+typedef struct mugiq_b200_loop_plan_s mugiq_b200_loop_plan_t;
+int mugiq_b200_loop_plan_create(mugiq_b200_loop_plan_t **plan, const void *gauge_d, const mugiq_b200_disp_entry_t *entries,
+                                int nentries, const mugiq_b200_geom_t *geom, void *stream);
+int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan);
+int mugiq_b200_loop_plan_nloop(const mugiq_b200_loop_plan_t *plan);
+int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed, int *nderived, int *ngroups,
+                              long long *wilson_bytes);
+int mugiq_b200_loop_plan_accumulate(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, const void *const *evec_d,
+                                    const double *sigma_h, int nvec, int accumulate, void *stream);
+int mugiq_b200_loop_plan_finalize(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, int accumulate, void *stream);
+
 /* ---- stage 3: gamma-basis / time-slice reorder -------------------------------------------------- */
 /* out[t + Lt*((15-G) + 16*iL) + Lt*nData*v3] = sign[G] * in[x_eo + V4*(G + 16*iL)].
  * Replaces convertIdxOrder_mapGamma (lib/contract_wrappers.cu:133-156,

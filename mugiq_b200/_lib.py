@@ -52,6 +52,12 @@ SYMBOLS = {
     "mugiq_b200_displace": (_i, [_vp, _vp, _vp, _i, _i, _pg, _vp]),
     "mugiq_b200_loop_workspace_bytes": (_ll, [_pg, _i, _pe, _i]),
     "mugiq_b200_loop_accumulate": (_i, [_vp, _pvp, _pd, _i, _vp, _pe, _i, _i, _vp, _pg, _vp]),
+    "mugiq_b200_loop_plan_create": (_i, [C.POINTER(_vp), _vp, _pe, _i, _pg, _vp]),
+    "mugiq_b200_loop_plan_destroy": (_i, [_vp]),
+    "mugiq_b200_loop_plan_nloop": (_i, [_vp]),
+    "mugiq_b200_loop_plan_info": (_i, [_vp, _pi, _pi, _pi, C.POINTER(_ll)]),
+    "mugiq_b200_loop_plan_accumulate": (_i, [_vp, _vp, _pvp, _pd, _i, _i, _vp]),
+    "mugiq_b200_loop_plan_finalize": (_i, [_vp, _vp, _i, _vp]),
     "mugiq_b200_reorder_mapgamma": (_i, [_vp, _vp, _i, _i, _pg, _vp]),
     "mugiq_b200_phase_matrix": (_i, [_vp, _pi, _i, _i, _pi, _pi, _pi, _i, _vp]),
     "mugiq_b200_momproj_workspace_bytes": (_ll, [_ll, _i, _ll, _i]),

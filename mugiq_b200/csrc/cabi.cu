@@ -39,6 +39,22 @@ static int check_dir_sign(int dir, int sign, const char *who) {
   return MUGIQ_B200_OK;
 }
 
+int check_entries(const mugiq_b200_disp_entry_t *entries, int nentries, const char *who) {
+  if (nentries < 0 || nentries > MUGIQ_B200_MAX_ENTRIES)
+    return set_error(MUGIQ_B200_EINVAL, "%s: nentries = %d out of range [0,%d]", who, nentries, MUGIQ_B200_MAX_ENTRIES);
+  if (nentries > 0 && !entries) return set_error(MUGIQ_B200_EINVAL, "%s: entries is NULL", who);
+  for (int e = 0; e < nentries; e++) {
+    int rc = check_dir_sign(entries[e].dir, entries[e].sign, who);
+    if (rc) return rc;
+    // LoopComputeParam swaps start/stop with a warning before the loop runs (include/loop_mugiq.h:234-239);
+    // at this level the entry must already be ordered
+    if (entries[e].start > entries[e].stop)
+      return set_error(MUGIQ_B200_EINVAL, "%s: entry %d has start %d > stop %d", who, e, entries[e].start,
+                       entries[e].stop);
+  }
+  return MUGIQ_B200_OK;
+}
+
 }  // namespace mugiq_b200
 
 using namespace mugiq_b200;
@@ -196,22 +212,6 @@ int mugiq_b200_displace(void *dst_d, const void *src_d, const void *gauge_d, int
   if (dst_d == src_d) return set_error(MUGIQ_B200_EINVAL, "%s: dst and src must differ", who);
   const LatGeom g = make_geom(geom->L);
   return displace(dst_d, src_d, gauge_d, dir, sign, g, geom->precision, (cudaStream_t)stream);
-}
-
-static int check_entries(const mugiq_b200_disp_entry_t *entries, int nentries, const char *who) {
-  if (nentries < 0 || nentries > MUGIQ_B200_MAX_ENTRIES)
-    return set_error(MUGIQ_B200_EINVAL, "%s: nentries = %d out of range [0,%d]", who, nentries, MUGIQ_B200_MAX_ENTRIES);
-  if (nentries > 0 && !entries) return set_error(MUGIQ_B200_EINVAL, "%s: entries is NULL", who);
-  for (int e = 0; e < nentries; e++) {
-    int rc = check_dir_sign(entries[e].dir, entries[e].sign, who);
-    if (rc) return rc;
-    // LoopComputeParam swaps start/stop with a warning before the loop runs (include/loop_mugiq.h:234-239);
-    // at this level the entry must already be ordered
-    if (entries[e].start > entries[e].stop)
-      return set_error(MUGIQ_B200_EINVAL, "%s: entry %d has start %d > stop %d", who, e, entries[e].start,
-                       entries[e].stop);
-  }
-  return MUGIQ_B200_OK;
 }
 
 long long mugiq_b200_loop_workspace_bytes(const mugiq_b200_geom_t *geom, int nvec,

@@ -1,0 +1,68 @@
+// fused.cuh — interface of the fused displace+contract kernel (fused_kernel.cu) and the gauge-only helper
+// kernels (wilson.cu) used by the loop schedule in loop_fused.cu.
+#pragma once
+#include "kernels.cuh"
+
+namespace mugiq_b200 {
+
+constexpr int kFusedMaxVec = 256;    // eigenvectors per launch (pointer + 1/sigma table travels as a kernel parameter)
+constexpr int kFusedMaxLoops = 4;    // displaced loops per launch group (the ultra-local loop rides along for free)
+constexpr int kFusedMaxRows = 4;     // lattice rows (fixed y,z,t; all x) per CTA tile
+constexpr int kFusedMaxSlots = kFusedMaxRows * (kFusedMaxLoops + 1);  // staged rows per eigenvector: own + shifted
+// 8 warps = 2 per SM sub-partition: each sub-partition owns 16384 registers, so 2 warps may use up to 255 registers
+// per thread (a third warp would cap the kernel at 168 and spill the 4x4 spin matrix + link + operands)
+constexpr int kFusedComputeWarps = 8;
+constexpr int kFusedThreads = kFusedComputeWarps * 32;
+
+// One displaced loop of a launch group: the kernel computes  M(x) += (1/sigma) conj(v(x)) (x) [W(x) v(x + sign*len*dir)]
+// where W is the Wilson line of `len` links (already daggered / shifted for minus), stored like one direction
+// of the gauge field: [x_eo][row][col] complex.
+struct FusedLoop {
+  const void *W;
+  long long out_off;  // complex offset of this loop's 16*V4 block in dataPos
+  int dir, sign, len;
+  int pad_;
+};
+
+struct FusedGroup {
+  FusedLoop loop[kFusedMaxLoops];
+  int nloops;
+};
+
+// Tile geometry chosen on the host (same for every CTA): NR = TY*TZ*TT rows per tile.
+struct FusedTiling {
+  int TY, TZ, TT, NR;
+  int nTy, nTz, nTt;     // tiles per dimension
+  int units;             // warps per loop: ceil(sitesPerTile / 32)
+  int nslots;            // staged rows per eigenvector (own + de-duplicated shifted rows), <= kFusedMaxSlots
+  int hr_stride;         // bytes between consecutive half-rows of a stage in shared memory
+  int stage_bytes;       // nslots * 2 * hr_stride
+  int nstages;
+  int skew;              // bytes of destination skew per (slot & 3): 16 = conflict-free reads, 0 = 128-B aligned rows
+};
+
+struct FusedVecTable {
+  const void *evec[kFusedMaxVec];
+  double inv_sigma[kFusedMaxVec];
+  int nvec;
+};
+
+// maximum number of displaced loops per group for this lattice / precision (warp and shared-memory budget)
+int fused_max_loops_per_group(const LatGeom &g, int precision);
+// Launches one group (0..kFusedMaxLoops displaced loops, plus the ultra-local loop if ul_off >= 0) over the whole
+// lattice for up to kFusedMaxVec eigenvectors.
+int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,
+                       const LatGeom &g, int precision, cudaStream_t stream);
+
+// ---- gauge-only helpers (wilson.cu) ---------------------------------------------------------------------
+// Wout(x) = Win(x) * U_dir(x + shift*dir)       (extends a plus-direction Wilson line by one link)
+int wilson_extend(void *Wout_d, const void *Win_d, const void *gauge_d, int dir, int shift, const LatGeom &g,
+                  int precision, cudaStream_t stream);
+// Wminus(x) = [Wplus(x - len*dir)]^dagger
+int wilson_minus_from_plus(void *Wminus_d, const void *Wplus_d, int dir, int len, const LatGeom &g, int precision,
+                           cudaStream_t stream);
+// loopMinus[G][x] (+)= herm(G) * conj(loopPlus[G][x - len*dir])   (Gamma_G^dagger = herm(G) Gamma_G)
+int loop_minus_from_plus(void *minus_d, const void *plus_d, int dir, int len, int accumulate, const LatGeom &g,
+                         int precision, cudaStream_t stream);
+
+}  // namespace mugiq_b200

@@ -25,6 +25,8 @@ inline double inv_sigma_of(double sigma, int precision) {
 
 inline size_t prec_bytes(int precision) { return precision == MUGIQ_B200_PREC_DOUBLE ? 8 : 4; }
 
+int check_entries(const mugiq_b200_disp_entry_t *entries, int nentries, const char *who);  // cabi.cu
+
 // stage 1
 int contract_batch(void *loop_d, const void *const *vL, const void *const *vR, const double *sigma, int nvec,
                    int accumulate, const LatGeom &g, int precision, cudaStream_t stream);

@@ -1,72 +1,353 @@
-// loop_fused.cu — stages 1+2 fused: the eigenvector / displacement loop nest of
-// Loop_Mugiq::computeCoarseLoop (/root/reference/lib/loop_mugiq.cpp:455-509).
+// loop_fused.cu — schedule of the eigenvector / displacement loop nest of Loop_Mugiq::computeCoarseLoop
+// (/root/reference/lib/loop_mugiq.cpp:455-509) on top of the fused kernel (fused_kernel.cu).
 //
-// Schedule "batched" (this file, v0): eigenvectors are processed in batches; per displacement entry the
-// whole batch is displaced hop by hop into a ping-pong workspace (one link load serves the batch) and
-// contracted with register accumulation over the batch, so the loop buffer is read-modified-written once
-// per batch and hop instead of once per eigenvector and hop.  The reference's per-hop blas::zero and the
-// two full field copies of Displace::swapAuxDispVec (lib/displace.cpp:47-52,59) are gone: the ping-pong
-// buffers swap by pointer.
-#include "kernels.cuh"
+// The reference runs, per displacement entry and per eigenvector, `stop` one-link hops (each: zero + kernel +
+// two field copies, lib/displace.cpp:47-67) and a contraction per requested length, re-traversing all
+// eigenvectors once per entry.  Here a LoopPlan is built once per (gauge field, entry list):
+//   1. the set of distinct (direction, sign, length) loops the entries request is collected;
+//   2. Wilson lines W_k are built from the links (wilson.cu), so each loop is one 3x3 multiply per site;
+//   3. a minus-direction loop whose plus-direction partner is also requested is not computed at all: it is
+//      derived from the partner's finished loop buffer (loop_minus_from_plus, exact identity);
+//      repeated requests of the same loop are copied;
+//   4. the remaining loops + the ultra-local loop are packed into launch groups of the fused kernel, which
+//      reads every eigenvector once per group and writes the loop buffer once per batch.
+// LoopPlan::accumulate() may be called for any number of eigenvector batches (shards, host-streamed batches);
+// LoopPlan::finalize() then fills the derived slots.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "fused.cuh"
 
 namespace mugiq_b200 {
 
-constexpr int kLoopBatch = 16;  // eigenvectors displaced together (workspace = 2 * kLoopBatch fields)
+struct LoopPlan {
+  struct Comp {  // a loop computed by the fused kernel
+    int dir, sign, len;
+    int iL;         // slot of dataPos it is written to
+    const void *W;  // Wilson line (device), nullptr for the ultra-local loop
+  };
+  struct Derive {  // a slot filled after the eigenvector sum
+    int kind;      // 0 = copy of slot src, 1 = minus from plus
+    int dst, src, dir, len;
+  };
+  LatGeom g;
+  int precision;
+  int nLoop;
+  bool symmetric;
+  std::vector<Comp> comps;
+  std::vector<Derive> derives;
+  std::vector<int> zero_slots;  // slots no hop reaches (start < 1): stay zero, as in the reference
+  std::vector<FusedGroup> groups;  // displaced loops; the ultra-local loop rides in groups[0]
+  // Wilson-line storage
+  struct WField {
+    int dir, sign, len;
+    size_t index;  // field index inside wbuf
+  };
+  std::vector<WField> wfields;
+  size_t nW = 0;
+  void *wbuf = nullptr;
+  bool own_wbuf = false;
 
-static size_t field_bytes(const LatGeom &g, int precision) {
-  return (size_t)g.volume * kSpinorLen * 2 * prec_bytes(precision);
+  size_t link_field_bytes() const { return (size_t)g.volume * kLinkLen * 2 * prec_bytes(precision); }
+  size_t loop_bytes() const { return (size_t)16 * g.volume * 2 * prec_bytes(precision); }
+  const void *wptr(size_t index) const { return static_cast<const char *>(wbuf) + index * link_field_bytes(); }
+};
+
+static bool env_flag(const char *name) {
+  const char *e = getenv(name);
+  return e && e[0] && e[0] != '0';
 }
 
+// Collects requested loops, decides what is computed / derived, sizes the Wilson-line storage.
+static const LoopPlan::WField *find_w(const LoopPlan &pl, int dir, int sign, int len) {
+  for (const LoopPlan::WField &w : pl.wfields)
+    if (w.dir == dir && w.sign == sign && w.len == len) return &w;
+  return nullptr;
+}
+
+// derive_ok: slots may be filled after the eigenvector sum (minus from plus, copies of repeated requests); false
+// when the call accumulates onto partial sums it did not produce itself, then every requested loop is computed.
+static void plan_layout(LoopPlan &pl, const LatGeom &g, int precision, const mugiq_b200_disp_entry_t *entries, int nentries,
+                        bool derive_ok) {
+  pl.g = g;
+  pl.precision = precision;
+  pl.symmetric = derive_ok && !env_flag("MUGIQ_B200_NO_PM_SYMMETRY");
+  pl.comps.clear();
+  pl.derives.clear();
+  pl.zero_slots.clear();
+  pl.wfields.clear();
+  struct Req {
+    int dir, sign, len, iL;
+  };
+  std::vector<Req> reqs;
+  int iL = 1;
+  for (int e = 0; e < nentries; e++) {
+    const mugiq_b200_disp_entry_t &en = entries[e];
+    const int nL = en.stop - en.start + 1;  // nLoopPerEntry, include/loop_mugiq.h:241
+    const int first = en.start < 1 ? 1 : en.start;
+    for (int s = 0; s < nL; s++) {
+      const int len = first + s;  // slot s holds the s-th contraction of the hop loop (dispCount, lib/loop_mugiq.cpp:492-495)
+      if (len <= en.stop)
+        reqs.push_back({en.dir, en.sign, len, iL + s});
+      else
+        pl.zero_slots.push_back(iL + s);
+    }
+    iL += nL;
+  }
+  pl.nLoop = iL;
+
+  auto find_comp = [&](int dir, int sign, int len) -> int {
+    for (size_t i = 0; i < pl.comps.size(); i++)
+      if (pl.comps[i].dir == dir && pl.comps[i].sign == sign && pl.comps[i].len == len) return (int)i;
+    return -1;
+  };
+  pl.comps.push_back({-1, 0, 0, 0, nullptr});  // ultra-local loop, slot 0
+  // pass 1: plus loops (and, without the symmetry, minus loops) are computed
+  for (const Req &r : reqs) {
+    if (r.sign == MUGIQ_B200_SIGN_MINUS && pl.symmetric) continue;
+    const int c = derive_ok ? find_comp(r.dir, r.sign, r.len) : -1;
+    if (c < 0)
+      pl.comps.push_back({r.dir, r.sign, r.len, r.iL, nullptr});
+    else
+      pl.derives.push_back({0, r.iL, pl.comps[c].iL, 0, 0});
+  }
+  // pass 2 (symmetric): a minus loop is derived from its plus partner if that is computed, else computed itself
+  if (pl.symmetric) {
+    for (const Req &r : reqs) {
+      if (r.sign != MUGIQ_B200_SIGN_MINUS) continue;
+      const int cp = find_comp(r.dir, MUGIQ_B200_SIGN_PLUS, r.len);
+      if (cp >= 0) {
+        pl.derives.push_back({1, r.iL, pl.comps[cp].iL, r.dir, r.len});
+        continue;
+      }
+      const int c = find_comp(r.dir, r.sign, r.len);
+      if (c < 0)
+        pl.comps.push_back({r.dir, r.sign, r.len, r.iL, nullptr});
+      else
+        pl.derives.push_back({0, r.iL, pl.comps[c].iL, 0, 0});
+    }
+  }
+  // Wilson lines: per direction the plus chain 2..kmax (k = 1 is the gauge field itself) and one field per
+  // computed minus loop
+  pl.nW = 0;
+  for (int dir = 0; dir < 4; dir++) {
+    int kmax = 0;
+    for (const LoopPlan::Comp &c : pl.comps)
+      if (c.dir == dir) kmax = std::max(kmax, c.len);
+    for (int k = 2; k <= kmax; k++) pl.wfields.push_back({dir, MUGIQ_B200_SIGN_PLUS, k, pl.nW++});
+    for (const LoopPlan::Comp &c : pl.comps)
+      if (c.dir == dir && c.sign == MUGIQ_B200_SIGN_MINUS && !find_w(pl, dir, MUGIQ_B200_SIGN_MINUS, c.len))
+        pl.wfields.push_back({dir, MUGIQ_B200_SIGN_MINUS, c.len, pl.nW++});
+  }
+}
+
+// Builds the Wilson lines into pl.wbuf and the launch groups.
+static int plan_build(LoopPlan &pl, const void *gauge_d, cudaStream_t stream) {
+  const size_t lfb = pl.link_field_bytes();
+  auto plus_ptr = [&](int dir, int len) -> const void * {
+    if (len == 1) return static_cast<const char *>(gauge_d) + (size_t)dir * lfb;
+    const LoopPlan::WField *w = find_w(pl, dir, MUGIQ_B200_SIGN_PLUS, len);
+    return w ? pl.wptr(w->index) : nullptr;
+  };
+  for (const LoopPlan::WField &w : pl.wfields) {  // ordered: plus chain ascending, then minus fields, per direction
+    void *dst = static_cast<char *>(pl.wbuf) + w.index * lfb;
+    int rc;
+    if (w.sign == MUGIQ_B200_SIGN_PLUS)  // W+_k(x) = W+_{k-1}(x) U(x + (k-1) mu)
+      rc = wilson_extend(dst, plus_ptr(w.dir, w.len - 1), gauge_d, w.dir, w.len - 1, pl.g, pl.precision, stream);
+    else  // W-_k(x) = [W+_k(x - k mu)]^dag
+      rc = wilson_minus_from_plus(dst, plus_ptr(w.dir, w.len), w.dir, w.len, pl.g, pl.precision, stream);
+    if (rc) return rc;
+  }
+  for (LoopPlan::Comp &c : pl.comps) {
+    if (c.dir < 0) continue;
+    if (c.sign == MUGIQ_B200_SIGN_PLUS)
+      c.W = plus_ptr(c.dir, c.len);
+    else
+      c.W = pl.wptr(find_w(pl, c.dir, MUGIQ_B200_SIGN_MINUS, c.len)->index);
+  }
+  // launch groups: ultra-local first, then loops sorted by (direction, length) so that loops sharing shifted
+  // rows land in the same group
+  const int maxl = fused_max_loops_per_group(pl.g, pl.precision);
+  if (maxl < 0 || (maxl < 1 && pl.comps.size() > 1))
+    return set_error(MUGIQ_B200_EINVAL, "loop plan: lattice %dx%dx%dx%d does not fit the fused kernel's tile", pl.g.L[0],
+                     pl.g.L[1], pl.g.L[2], pl.g.L[3]);
+  std::vector<LoopPlan::Comp> order(pl.comps.begin(), pl.comps.end());
+  std::stable_sort(order.begin() + 1, order.end(), [](const LoopPlan::Comp &a, const LoopPlan::Comp &b) {
+    if (a.dir != b.dir) return a.dir < b.dir;
+    if (a.sign != b.sign) return a.sign > b.sign;
+    return a.len < b.len;
+  });
+  pl.groups.clear();
+  const size_t per_loop = (size_t)16 * pl.g.volume;
+  size_t i = 1;  // order[0] is the ultra-local loop
+  do {
+    FusedGroup grp;
+    grp.nloops = maxl > 0 ? (int)std::min<size_t>(maxl, order.size() - i) : 0;
+    for (int j = 0; j < grp.nloops; j++) {
+      const LoopPlan::Comp &c = order[i + j];
+      grp.loop[j].W = c.W;
+      grp.loop[j].out_off = (long long)(per_loop * c.iL);
+      grp.loop[j].dir = c.dir;
+      grp.loop[j].sign = c.sign == MUGIQ_B200_SIGN_PLUS ? +1 : -1;
+      grp.loop[j].len = c.len;
+      grp.loop[j].pad_ = 0;
+    }
+    pl.groups.push_back(grp);
+    i += grp.nloops;
+  } while (i < order.size());
+  return MUGIQ_B200_OK;
+}
+
+static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
+                           int accumulate, cudaStream_t stream) {
+  char *pos = static_cast<char *>(dataPos_d);
+  if (!accumulate)
+    for (int z : pl.zero_slots) MUGIQ_CUDA_CHECK(cudaMemsetAsync(pos + (size_t)z * pl.loop_bytes(), 0, pl.loop_bytes(), stream));
+  for (int done = 0; done < nvec; done += kFusedMaxVec) {
+    FusedVecTable vt;
+    vt.nvec = std::min(kFusedMaxVec, nvec - done);
+    for (int i = 0; i < vt.nvec; i++) {
+      vt.evec[i] = evec_d[done + i];
+      vt.inv_sigma[i] = inv_sigma_of(sigma_h[done + i], pl.precision);
+    }
+    for (size_t gi = 0; gi < pl.groups.size(); gi++) {
+      // slot 0 (ultra-local) is accumulated by the first group
+      int rc = fused_group_launch(dataPos_d, pl.groups[gi], gi == 0 ? 0 : -1, vt, accumulate || done > 0, pl.g,
+                                  pl.precision, stream);
+      if (rc) return rc;
+    }
+  }
+  return MUGIQ_B200_OK;
+}
+
+static int plan_finalize(const LoopPlan &pl, void *dataPos_d, int accumulate, cudaStream_t stream) {
+  char *pos = static_cast<char *>(dataPos_d);
+  const size_t lb = pl.loop_bytes();
+  for (const LoopPlan::Derive &d : pl.derives) {
+    if (d.kind == 1) {
+      int rc = loop_minus_from_plus(pos + (size_t)d.dst * lb, pos + (size_t)d.src * lb, d.dir, d.len, accumulate, pl.g,
+                                    pl.precision, stream);
+      if (rc) return rc;
+    }
+  }
+  // copies last: a copy source may itself be a derived slot only through `repeated` requests of computed loops,
+  // which are resolved against computed slots above, so order does not matter beyond kind
+  for (const LoopPlan::Derive &d : pl.derives) {
+    if (d.kind == 0) {
+      if (accumulate)
+        return set_error(MUGIQ_B200_EINVAL, "loop plan: repeated entries cannot be finalized in accumulate mode");
+      MUGIQ_CUDA_CHECK(cudaMemcpyAsync(pos + (size_t)d.dst * lb, pos + (size_t)d.src * lb, lb, cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  return MUGIQ_B200_OK;
+}
+
+// ---- one-shot entry points (kernels.cuh) ---------------------------------------------------------------------
 long long loop_workspace_bytes(const LatGeom &g, int precision, int nvec, const mugiq_b200_disp_entry_t *entries,
                                int nentries) {
-  (void)entries;
+  (void)nvec;
   if (nentries <= 0) return 0;
-  const int nb = nvec < kLoopBatch ? nvec : kLoopBatch;
-  return (long long)(2 * (size_t)nb * field_bytes(g, precision));
+  // the non-symmetric layout needs the most Wilson lines; the one-shot call may use either
+  LoopPlan a, b;
+  plan_layout(a, g, precision, entries, nentries, true);
+  plan_layout(b, g, precision, entries, nentries, false);
+  return (long long)(std::max(a.nW, b.nW) * a.link_field_bytes());
 }
 
 int loop_accumulate(void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec, const void *gauge_d,
                     const mugiq_b200_disp_entry_t *entries, int nentries, int accumulate, void *workspace_d,
                     const LatGeom &g, int precision, cudaStream_t stream) {
-  const size_t loop_bytes = (size_t)16 * g.volume * 2 * prec_bytes(precision);  // one loop (16 gammas)
-  char *pos = static_cast<char *>(dataPos_d);
-
-  // iL = 0: ultra-local, vR = vL   (lib/loop_mugiq.cpp:499-503)
-  int rc = contract_batch(pos, evec_d, nullptr, sigma_h, nvec, accumulate, g, precision, stream);
+  LoopPlan pl;
+  // accumulating onto partial sums: the minus slots cannot be derived from accumulated plus slots, compute them
+  plan_layout(pl, g, precision, entries, nentries, accumulate == 0);
+  if (pl.nW > 0 && !workspace_d) return set_error(MUGIQ_B200_EINVAL, "loop_accumulate: workspace_d is NULL");
+  pl.wbuf = workspace_d;
+  int rc = plan_build(pl, gauge_d, stream);
   if (rc) return rc;
-  if (nentries == 0) return MUGIQ_B200_OK;
-  if (!workspace_d) return set_error(MUGIQ_B200_EINVAL, "loop_accumulate: workspace_d is NULL");
-
-  const size_t fb = field_bytes(g, precision);
-  int iL = 1;
-  for (int e = 0; e < nentries; e++) {
-    const mugiq_b200_disp_entry_t &en = entries[e];
-    const int nL = en.stop - en.start + 1;  // nLoopPerEntry, include/loop_mugiq.h:241
-    // the reference zeroes the entry's slots (lib/loop_mugiq.cpp:476) and fills them in the order the
-    // contractions happen (dispCount), so slots that no hop reaches (start < 1) stay zero
-    if (!accumulate) MUGIQ_CUDA_CHECK(cudaMemsetAsync(pos + (size_t)iL * loop_bytes, 0, (size_t)nL * loop_bytes, stream));
-    for (int b0 = 0; b0 < nvec; b0 += kLoopBatch) {
-      const int nb = (nvec - b0 < kLoopBatch) ? nvec - b0 : kLoopBatch;
-      const void *src[kLoopBatch];
-      void *dst[kLoopBatch];
-      for (int i = 0; i < nb; i++) src[i] = evec_d[b0 + i];
-      int dispCount = 0;
-      for (int k = 1; k <= en.stop; k++) {
-        for (int i = 0; i < nb; i++) dst[i] = static_cast<char *>(workspace_d) + ((size_t)(k & 1) * nb + i) * fb;
-        rc = displace_batch(dst, src, nb, gauge_d, en.dir, en.sign, g, precision, stream);
-        if (rc) return rc;
-        for (int i = 0; i < nb; i++) src[i] = dst[i];
-        if (k >= en.start && dispCount < nL) {
-          rc = contract_batch(pos + (size_t)(iL + dispCount) * loop_bytes, evec_d + b0, src, sigma_h + b0, nb, 1, g,
-                              precision, stream);
-          if (rc) return rc;
-          dispCount++;
-        }
-      }
-    }
-    iL += nL;
-  }
-  return MUGIQ_B200_OK;
+  if ((rc = plan_accumulate(pl, dataPos_d, evec_d, sigma_h, nvec, accumulate, stream))) return rc;
+  return plan_finalize(pl, dataPos_d, 0, stream);
 }
 
 }  // namespace mugiq_b200
+
+// ---- plan C-ABI (include/mugiq_b200.h) ---------------------------------------------------------------------------
+using namespace mugiq_b200;
+
+struct mugiq_b200_loop_plan_s {
+  LoopPlan pl;
+};
+
+extern "C" {
+
+int mugiq_b200_loop_plan_create(mugiq_b200_loop_plan_t **plan, const void *gauge_d, const mugiq_b200_disp_entry_t *entries,
+                                int nentries, const mugiq_b200_geom_t *geom, void *stream) {
+  const char *who = "mugiq_b200_loop_plan_create";
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "%s: plan is NULL", who);
+  *plan = nullptr;
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  if ((rc = check_entries(entries, nentries, who))) return rc;
+  if (nentries > 0 && !gauge_d) return set_error(MUGIQ_B200_EINVAL, "%s: gauge_d is NULL", who);
+  mugiq_b200_loop_plan_s *p = new mugiq_b200_loop_plan_s;
+  plan_layout(p->pl, make_geom(geom->L), geom->precision, entries, nentries, true);
+  if (p->pl.nW > 0) {
+    if (cudaMalloc(&p->pl.wbuf, p->pl.nW * p->pl.link_field_bytes()) != cudaSuccess) {
+      cudaGetLastError();
+      const size_t want = p->pl.nW * p->pl.link_field_bytes();
+      delete p;
+      return set_error(MUGIQ_B200_ENOMEM, "%s: cannot allocate %zu bytes of Wilson-line storage", who, want);
+    }
+    p->pl.own_wbuf = true;
+  }
+  rc = plan_build(p->pl, gauge_d, (cudaStream_t)stream);
+  if (rc) {
+    if (p->pl.own_wbuf) cudaFree(p->pl.wbuf);
+    delete p;
+    return rc;
+  }
+  *plan = p;
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan) {
+  if (!plan) return MUGIQ_B200_OK;
+  if (plan->pl.own_wbuf && plan->pl.wbuf) cudaFree(plan->pl.wbuf);
+  delete plan;
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_loop_plan_nloop(const mugiq_b200_loop_plan_t *plan) {
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_loop_plan_nloop: plan is NULL");
+  return plan->pl.nLoop;
+}
+
+int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed, int *nderived, int *ngroups,
+                              long long *wilson_bytes) {
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_loop_plan_info: plan is NULL");
+  if (ncomputed) *ncomputed = (int)plan->pl.comps.size();
+  if (nderived) *nderived = (int)plan->pl.derives.size();
+  if (ngroups) *ngroups = (int)plan->pl.groups.size();
+  if (wilson_bytes) *wilson_bytes = (long long)(plan->pl.nW * plan->pl.link_field_bytes());
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_loop_plan_accumulate(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, const void *const *evec_d,
+                                    const double *sigma_h, int nvec, int accumulate, void *stream) {
+  const char *who = "mugiq_b200_loop_plan_accumulate";
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "%s: plan is NULL", who);
+  if (!dataPos_d || !evec_d || !sigma_h) return set_error(MUGIQ_B200_EINVAL, "%s: NULL argument", who);
+  if (nvec < 1) return set_error(MUGIQ_B200_EINVAL, "%s: nvec = %d must be positive", who, nvec);
+  for (int i = 0; i < nvec; i++)
+    if (!evec_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: eigenvector %d is NULL", who, i);
+  return plan_accumulate(plan->pl, dataPos_d, evec_d, sigma_h, nvec, accumulate, (cudaStream_t)stream);
+}
+
+int mugiq_b200_loop_plan_finalize(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, int accumulate, void *stream) {
+  const char *who = "mugiq_b200_loop_plan_finalize";
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "%s: plan is NULL", who);
+  if (!dataPos_d) return set_error(MUGIQ_B200_EINVAL, "%s: dataPos_d is NULL", who);
+  return plan_finalize(plan->pl, dataPos_d, accumulate, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -65,6 +65,7 @@ class Displace:
         self.L = tuple(int(x) for x in L)
         self.device = device
         self.gaugeField = None
+        self.gaugeVersion = 0
         self.upload_gauge(loopParams)
         self.auxDispVec = torch.zeros((Lattice(self.L).volume, 12), dtype=dtype, device=device)
         self.dispString = ""
@@ -77,6 +78,7 @@ class Displace:
             self.gaugeField = ops.gauge_upload(loopParams.gauge, self.L, device=self.device)
         else:
             ops.gauge_upload(loopParams.gauge, self.L, device=self.device, out=self.gaugeField)
+        self.gaugeVersion += 1
         return self.gaugeField
 
     def setupDisplacement(self, dStr: str):
@@ -142,7 +144,8 @@ class Loop_Mugiq:
             self._createPhaseMatrix()
         if self.cPrm.doNonLocal:
             self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
-        self._workspace = None
+        self._plan = None
+        self._plan_version = -1
 
     # -- lib/loop_mugiq.cpp:102-158 ---------------------------------------------------------------------
     def _allocateDataMemory(self):
@@ -166,20 +169,17 @@ class Loop_Mugiq:
     def computeCoarseLoop(self):
         p = self.cPrm
         es = self.eigsolve
-        entries = p.entries() if p.doNonLocal else []
-        gauge = self.displace.gaugeField if self.displace is not None else None
-        nb_ws = self.evec_batch if es.eVecs[0].is_cuda else self.stream_batch
-        need = ops.loop_workspace_bytes(self.L, self.precision, min(es.nEv, nb_ws), entries)
-        if need > 0 and (self._workspace is None or self._workspace.numel() < need):
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
+            plan = self._loop_plan()
             if es.eVecs[0].is_cuda:
                 for b0 in range(0, es.nEv, self.evec_batch):
                     b1 = min(es.nEv, b0 + self.evec_batch)
-                    ops.loop_accumulate(self.dataPos_d, es.eVecs[b0:b1], es.eVals_sigma[b0:b1], gauge, entries, self.L,
-                                        accumulate=b0 > 0, workspace=self._workspace)
+                    plan.accumulate(self.dataPos_d, es.eVecs[b0:b1], es.eVals_sigma[b0:b1], accumulate=b0 > 0)
             else:
-                self._accumulate_from_host(entries, gauge)
+                self._accumulate_from_host(plan)
+            # slots derived after the eigenvector sum (minus-direction partners, repeated entries); linear, so
+            # it commutes with the cross-rank sum below
+            plan.finalize(self.dataPos_d)
             # eigenvector shards: the position-space buffer is summed over the group only when it is
             # needed on every rank (host copy requested or no momentum projection); otherwise the
             # projection, which is linear, runs on the partial sums and the small dataMom is reduced
@@ -197,7 +197,21 @@ class Loop_Mugiq:
                 self.performMomentumProjection()
         return self
 
-    def _accumulate_from_host(self, entries, gauge):
+    def _loop_plan(self):
+        """The Wilson lines + launch schedule for (gauge field, entries): built once, rebuilt when the gauge field
+        is uploaded again (Displace.upload_gauge bumps gaugeVersion)."""
+        p = self.cPrm
+        version = self.displace.gaugeVersion if self.displace is not None else 0
+        if self._plan is None or self._plan_version != version:
+            if self._plan is not None:
+                self._plan.close()
+            entries = p.entries() if p.doNonLocal else []
+            gauge = self.displace.gaugeField if self.displace is not None else None
+            self._plan = ops.LoopPlan(gauge, entries, self.L, self.precision)
+            self._plan_version = version
+        return self._plan
+
+    def _accumulate_from_host(self, plan):
         """Eigenvectors resident in (pinned) HOST memory: double-buffered H2D copies of eigenvector batches on a
         copy stream overlap the loop kernels of the previous batch."""
         es = self.eigsolve
@@ -226,8 +240,7 @@ class Loop_Mugiq:
                 issue(i + 1)
             s = i & 1
             main.wait_event(ready[s])
-            ops.loop_accumulate(self.dataPos_d, [stage[s][k] for k in range(b1 - b0)], es.eVals_sigma[b0:b1], gauge,
-                                entries, self.L, accumulate=i > 0, workspace=self._workspace)
+            plan.accumulate(self.dataPos_d, [stage[s][k] for k in range(b1 - b0)], es.eVals_sigma[b0:b1], accumulate=i > 0)
             freed[s].record(main)
 
     # -- lib/loop_mugiq.cpp:323-434 ---------------------------------------------------------------------

@@ -143,6 +143,56 @@ def loop_accumulate(dataPos, evecs, sigma, gauge, entries, L, accumulate=False, 
     return dataPos
 
 
+class LoopPlan:
+    """mugiq_b200_loop_plan_*: owns the Wilson lines and the launch schedule for one (gauge field, entry list)."""
+
+    def __init__(self, gauge, entries, L, precision=PREC_DOUBLE):
+        self.L = tuple(int(x) for x in L)
+        self.precision = precision
+        self._gauge = gauge  # keep the device gauge field alive: one-link loops read it directly
+        self._h = C.c_void_p()
+        if gauge is not None:
+            _dev(gauge)
+        geom = make_geom(L, precision)
+        dev = gauge.device if gauge is not None else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            check(_lib.load().mugiq_b200_loop_plan_create(C.byref(self._h), gauge.data_ptr() if gauge is not None else None,
+                                                          entry_array(entries), len(entries), C.byref(geom), _stream()))
+        self.nLoop = check(_lib.load().mugiq_b200_loop_plan_nloop(self._h))
+
+    def info(self):
+        a, b, c, w = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        check(_lib.load().mugiq_b200_loop_plan_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(w)))
+        return {"computed": a.value, "derived": b.value, "groups": c.value, "wilson_bytes": w.value}
+
+    def accumulate(self, dataPos, evecs, sigma, accumulate=False):
+        _dev(dataPos, *evecs)
+        n = len(evecs)
+        sig = (C.c_double * n)(*[float(s) for s in sigma])
+        with torch.cuda.device(dataPos.device):
+            check(_lib.load().mugiq_b200_loop_plan_accumulate(self._h, dataPos.data_ptr(),
+                                                              ptr_array([v.data_ptr() for v in evecs]), sig, n,
+                                                              int(bool(accumulate)), _stream()))
+        return dataPos
+
+    def finalize(self, dataPos, accumulate=False):
+        _dev(dataPos)
+        with torch.cuda.device(dataPos.device):
+            check(_lib.load().mugiq_b200_loop_plan_finalize(self._h, dataPos.data_ptr(), int(bool(accumulate)), _stream()))
+        return dataPos
+
+    def close(self):
+        if self._h:
+            _lib.load().mugiq_b200_loop_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def reorder_mapgamma(out, inp, nData, nLoop, L):
     _dev(out, inp)
     geom = make_geom(L, _prec(inp))

@@ -53,6 +53,6 @@ def test_argument_validation_without_gpu():
     assert lib.mugiq_b200_loop_workspace_bytes(ctypes.byref(g), 4, _lib.entry_array([(4, 1, 1, 1)]), 1) == -1
     assert lib.mugiq_b200_loop_workspace_bytes(ctypes.byref(g), 4, _lib.entry_array([(0, 1, 3, 1)]), 1) == -1
     assert lib.mugiq_b200_loop_workspace_bytes(ctypes.byref(g), 4, _lib.entry_array([]), 0) == 0
-    assert lib.mugiq_b200_loop_workspace_bytes(ctypes.byref(g), 4, _lib.entry_array([(0, 1, 1, 1)]), 1) > 0
+    assert lib.mugiq_b200_loop_workspace_bytes(ctypes.byref(g), 4, _lib.entry_array([(0, 1, 1, 2)]), 1) > 0
     assert lib.mugiq_b200_momproj_workspace_bytes(0, 1, 1, 8) == -1
     assert lib.mugiq_b200_momproj_workspace_bytes(4608, 33, 4096, 8) > 0

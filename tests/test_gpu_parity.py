@@ -130,6 +130,58 @@ def test_loop_accumulate_matches_oracle(ops, oracle, L, name):
     assert rel_err(host(out2), ref) < TOL_F64
 
 
+LOOP_LATTICES = [(16, 4, 4, 4), (12, 2, 4, 2), (6, 4, 2, 4), (24, 2, 2, 2), (4, 4, 4, 8), (8, 2, 2, 3)]
+
+
+@pytest.mark.parametrize("L", LOOP_LATTICES)
+@pytest.mark.parametrize("name", ["onehop8", "ranges", "repeated"])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_loop_plan_batches(ops, oracle, L, name, symmetric, monkeypatch):
+    """Plan form: Wilson lines built once, eigenvectors fed in three batches, derived slots filled by finalize;
+    with and without the minus-from-plus identity; lattices exercising every lane->site mapping of the fused
+    kernel (Lx/2 = 8, 6, 3, 12, 2, 4; tiles 2x2x1, 2x1x2, 1x2x2 ...)."""
+    if not symmetric:
+        monkeypatch.setenv("MUGIQ_B200_NO_PM_SYMMETRY", "1")
+    entries = ENTRY_SETS[name]
+    nEv = 7
+    ev = synth.random_evecs_np(L, nEv, seed=41)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=41)
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    gd = ops.gauge_upload(U, L)
+    evd = [dev(ev[i]) for i in range(nEv)]
+    plan = ops.LoopPlan(gd, entries, L)
+    info = plan.info()
+    assert plan.nLoop == ref.shape[0]
+    if symmetric and name == "onehop8":
+        assert info["computed"] == 5 and info["derived"] == 4 and info["wilson_bytes"] == 0
+    if not symmetric and name == "onehop8":
+        assert info["computed"] == 9 and info["derived"] == 0
+    out = torch.full(ref.shape, 5.0 - 2.0j, dtype=torch.complex128, device="cuda")
+    plan.accumulate(out, evd[:3], sig[:3], accumulate=False)
+    plan.accumulate(out, evd[3:4], sig[3:4], accumulate=True)
+    plan.accumulate(out, evd[4:], sig[4:], accumulate=True)
+    plan.finalize(out)
+    assert rel_err(host(out), ref) < TOL_F64
+    plan.close()
+
+
+def test_loop_plan_many_vectors(ops, oracle):
+    """More eigenvectors than one launch's pointer table (kFusedMaxVec = 256): chunked launches accumulate."""
+    L = (4, 2, 2, 2)
+    nEv = 300
+    ev = synth.random_evecs_np(L, nEv, seed=42)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=42)
+    entries = [(1, 1, 1, 2), (1, 0, 2, 2)]
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    gd = ops.gauge_upload(U, L)
+    evd = dev(ev)
+    out = torch.zeros(ref.shape, dtype=torch.complex128, device="cuda")
+    ops.loop_accumulate(out, list(evd), sig, gd, entries, L)
+    assert rel_err(host(out), ref) < TOL_F64
+
+
 def test_loop_accumulate_float(ops, oracle):
     L = (4, 4, 4, 8)
     entries = ENTRY_SETS["onehop8"] + [(3, 1, 2, 3)]
@@ -187,7 +239,8 @@ def test_phase_matrix(ops, oracle, prec, ftsign):
     mom = momenta_up_to(4)
     ref = oracle.phase_matrix(mom, ftsign, L, tot, cc, dtype=cdt(prec))
     out = ops.phase_matrix(mom, ftsign, L, tot, cc, dtype=torch.complex128 if prec == 8 else torch.complex64)
-    assert np.abs(host(out) - ref).max() < (4e-15 if prec == 8 else 3e-7)
+    # FP32: the reference (and the oracle) accumulate the phase in float, this kernel in double before rounding
+    assert np.abs(host(out) - ref).max() < (4e-15 if prec == 8 else 5e-6)
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 1, 64), (4608, 1, 4096), (96, 7, 128), (1000, 19, 333), (512, 33, 512),
