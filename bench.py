@@ -276,7 +276,16 @@ def run_ours(args, wl, name):
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(dom, {}).get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        fp64 = None
+        if d.get("alg_flops", 0) > 0:
+            mb = os.path.join(ROOT, "profiles", "r1_microbench_b200.json")
+            fp64_peak = json.load(open(mb))["dfma_tflops"] if os.path.exists(mb) else 34.15
+            tf = d["alg_flops"] / d["launches"] / (per_launch_ms * 1e-3) / 1e12
+            fp64 = {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                    "peak_source": "measured DFMA stream, tools/microbench.cu (profiles/r1_microbench_b200.json)",
+                    "note": "the fused kernel is FP64-pipe bound (15 flop per compulsory byte, ridge 5.2): this fraction, "
+                            "not the HBM one, measures its distance from the speed of light (DESIGN.md 4.1)"}
+        roofline = {"bound": "hbm", "kernel": dom, "fp64": fp64, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                     "share_of_step": d["ms"] / (ms_step * args.steps),

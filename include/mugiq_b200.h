@@ -202,13 +202,14 @@ int mugiq_b200_momproj(void *mom_d, const void *posMP_d, const void *phase_d, lo
 /* Per-kernel launch counters (always on) and CUDA-event timers (while enabled) around every kernel launch
  * of the library, recorded on the stream the kernel is launched on.  The reference only brackets
  * init/total/free with QUDA TimeProfile (lib/interface_mugiq.cpp:36-47,193-244).  prof_query synchronises
- * on the recorded events; alg_bytes_total is the ALGORITHMIC byte count of the timed launches. */
+ * on the recorded events; alg_bytes_total / alg_flops_total are the ALGORITHMIC byte and FP64 flop counts of the
+ * launches (FMA = 2 flop). */
 int mugiq_b200_prof_enable(int on);
 int mugiq_b200_prof_reset(void);
 int mugiq_b200_prof_num_kernels(void);
 const char *mugiq_b200_prof_name(int kernel_id);
 int mugiq_b200_prof_query(int kernel_id, long long *launches, long long *timed_launches, double *ms_total,
-                          double *alg_bytes_total);
+                          double *alg_bytes_total, double *alg_flops_total);
 
 #ifdef __cplusplus
 }

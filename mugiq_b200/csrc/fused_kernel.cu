@@ -595,7 +595,11 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   // algorithmic (compulsory) bytes: every eigenvector site once, every link once, the accumulators once
   const double S = 24.0 * sizeof(F), U = 18.0 * sizeof(F), Acc = 32.0 * sizeof(F);
   const int nl = grp.nloops + (ul_off >= 0 ? 1 : 0);
-  ProfScope prof(K_LOOP_FUSED, stream, (double)g.volume * (vt.nvec * S + grp.nloops * U + nl * Acc * (accumulate ? 2 : 1)));
+  // FP64 work per (eigvec, site): 336 DFMA + 24 DMUL per displaced loop (W v: 144, scale: 24, colour trace: 192) and
+  // 96 DFMA for the Hermitian ultra-local matrix (+24 DMUL when it runs alone); FMA = 2 flop
+  const double flop_site = grp.nloops * (336.0 * 2 + 24.0) + (ul_off >= 0 ? 96.0 * 2 + (grp.nloops == 0 ? 24.0 : 0.0) : 0.0);
+  ProfScope prof(K_LOOP_FUSED, stream, (double)g.volume * (vt.nvec * S + grp.nloops * U + nl * Acc * (accumulate ? 2 : 1)),
+                 (double)g.volume * vt.nvec * flop_site);
   switch (grp.nloops) {
     case 0: return launch_fused_nd<F, 0>(args, smem, stream);
     case 1: return launch_fused_nd<F, 1>(args, smem, stream);

@@ -183,7 +183,8 @@ int momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, 
   if (!workspace_d) return set_error(MUGIQ_B200_EINVAL, "momproj: workspace_d is NULL");
   {
   // algorithmic bytes: A once, phase once, result once; flops 8*M*N*K are reported by the caller
-  ProfScope prof(K_MOMPROJ, stream, 2.0 * prec_bytes(precision) * ((double)M * K + (double)K * N + (double)M * N));
+  ProfScope prof(K_MOMPROJ, stream, 2.0 * prec_bytes(precision) * ((double)M * K + (double)K * N + (double)M * N),
+                 8.0 * (double)M * N * (double)K);
   if (precision == MUGIQ_B200_PREC_DOUBLE && !use_simt()) {
     const int NT = nt_for(N);
     const dim3 grid((unsigned)((M + kRowsPerCta - 1) / kRowsPerCta), ks, (N + NT * 4 - 1) / (NT * 4));

@@ -17,6 +17,7 @@ struct ProfState {
   bool enabled = false;
   long long launches[K_COUNT] = {0};
   double bytes[K_COUNT] = {0};
+  double flops[K_COUNT] = {0};
   double ms[K_COUNT] = {0};          // resolved time
   long long timed[K_COUNT] = {0};    // launches with resolved time
   std::vector<EventPair> pending;    // recorded, not yet resolved
@@ -34,11 +35,12 @@ const char *kNames[K_COUNT] = {"contract_batch", "displace",      "loop_fused", 
 
 const char *kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kNames[id] : "?"; }
 
-void prof_begin(int id, cudaStream_t stream, double alg_bytes) {
+void prof_begin(int id, cudaStream_t stream, double alg_bytes, double alg_flops) {
   ProfState &s = st();
   std::lock_guard<std::mutex> lk(s.mu);
   s.launches[id]++;
   s.bytes[id] += alg_bytes;
+  s.flops[id] += alg_flops;
   if (!s.enabled) return;
   EventPair ep;
   if (!s.pool.empty()) {
@@ -93,7 +95,7 @@ int mugiq_b200_prof_reset(void) {
   resolve_locked(s);
   for (int i = 0; i < K_COUNT; i++) {
     s.launches[i] = s.timed[i] = 0;
-    s.bytes[i] = s.ms[i] = 0;
+    s.bytes[i] = s.flops[i] = s.ms[i] = 0;
   }
   return MUGIQ_B200_OK;
 }
@@ -103,7 +105,7 @@ int mugiq_b200_prof_num_kernels(void) { return K_COUNT; }
 const char *mugiq_b200_prof_name(int kernel_id) { return kernel_name(kernel_id); }
 
 int mugiq_b200_prof_query(int kernel_id, long long *launches, long long *timed_launches, double *ms_total,
-                          double *alg_bytes_total) {
+                          double *alg_bytes_total, double *alg_flops_total) {
   if (kernel_id < 0 || kernel_id >= K_COUNT)
     return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_prof_query: kernel id %d out of range", kernel_id);
   ProfState &s = st();
@@ -113,6 +115,7 @@ int mugiq_b200_prof_query(int kernel_id, long long *launches, long long *timed_l
   if (timed_launches) *timed_launches = s.timed[kernel_id];
   if (ms_total) *ms_total = s.ms[kernel_id];
   if (alg_bytes_total) *alg_bytes_total = s.bytes[kernel_id];
+  if (alg_flops_total) *alg_flops_total = s.flops[kernel_id];
   return MUGIQ_B200_OK;
 }
 

@@ -24,13 +24,15 @@ enum KernelId {
 
 const char *kernel_name(int id);
 // Called by launch sites.  Always counts the launch; records events only while profiling is enabled.
-void prof_begin(int id, cudaStream_t stream, double alg_bytes);
+void prof_begin(int id, cudaStream_t stream, double alg_bytes, double alg_flops);
 void prof_end(int id, cudaStream_t stream);
 
 struct ProfScope {
   int id;
   cudaStream_t stream;
-  ProfScope(int id_, cudaStream_t s, double alg_bytes = 0.0) : id(id_), stream(s) { prof_begin(id, s, alg_bytes); }
+  ProfScope(int id_, cudaStream_t s, double alg_bytes = 0.0, double alg_flops = 0.0) : id(id_), stream(s) {
+    prof_begin(id, s, alg_bytes, alg_flops);
+  }
   ~ProfScope() { prof_end(id, stream); }
 };
 

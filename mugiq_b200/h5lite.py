@@ -18,3 +18,21 @@ def write_momentum_loops(filename, loop):
     if not filename:
         raise ValueError("write_momentum_loops: empty filename (option --loop-mom-space-filename)")
     np.savez(filename, **momentum_loop_datasets(loop))
+
+
+def read_loops_file(path):
+    """Reads the flat loop file the C++ host mirror writes (Loop_Mugiq::writeLoopsHDF5_Mom in
+    mugiq_b200/host/src/loop_mugiq.cpp): text index + raw values.  Returns {hdf5 path: complex array [T]}."""
+    with open(path, "rb") as fh:
+        blob = fh.read()
+    end = blob.index(b"end\n") + 4
+    lines = blob[:end].decode().splitlines()
+    if not lines[0].startswith("MUGIQ-B200 LOOPS v1"):
+        raise ValueError(f"{path}: not a mugiq_b200 loop file")
+    dt = np.float64 if lines[0].split()[-1] == "f64" else np.float32
+    out = {}
+    for ln in lines[1:-1]:
+        _, name, T, off = ln.split()
+        v = np.frombuffer(blob, dtype=dt, count=2 * int(T), offset=end + int(off)).reshape(int(T), 2)
+        out[name] = v[:, 0] + 1j * v[:, 1]
+    return out

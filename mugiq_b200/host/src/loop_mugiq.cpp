@@ -1,0 +1,343 @@
+// loop_mugiq.cpp — Loop_Mugiq<Float,fieldOrder> (/root/reference/lib/loop_mugiq.cpp).
+//
+// What is kept: constructor order (compute params -> comms -> buffers -> gamma tables -> phase matrix -> Displace,
+// lib/loop_mugiq.cpp:7-59), buffer sizes and index orders (:102-158), the "always copy dataPos to the host" rule
+// (:512), the call-once momentum projection (:325,433), the write-flag fix-ups (:669-693), fatal errors.
+// What differs on purpose: the eigenvector x displacement loop nest (:455-509) is the LoopPlan of the CUDA library
+// (one fused kernel per launch group and eigenvector batch instead of 4-6 synchronous launches and 3 field copies
+// per eigenvector and hop); cuBLAS Zgemm/Cgemm (:364-377) is mugiq_b200_momproj; MPI and HDF5 are absent (single
+// process; the loop file is the flat format of writeLoopsHDF5_Mom below).
+#include "loop_mugiq.h"
+
+#include <cstring>
+#include <fstream>
+
+#include "host_util.h"
+
+template <typename Float, QudaFieldOrder fieldOrder> struct Loop_Mugiq<Float, fieldOrder>::LoopComputeParam {
+  const int nG = N_GAMMA_;
+  const int momDim = MOM_DIM_;
+  int Nmom;
+  LoopFTSign FTSign;
+  std::vector<int> momMatrix;  // MOM_MATRIX_IDX(id, im) order
+  MuGiqBool doMomProj, doNonLocal;
+  int localL[N_DIM_], totalL[N_DIM_];
+  int nParity, volumeCB;
+  int locT = 0, totT = 0;
+  long long locV4 = 1, locV3 = 1, totV3 = 1;
+  LoopCalcType calcType;
+  int nDispEntries = 0;
+  std::vector<std::string> dispEntry, dispString;
+  std::vector<int> dispStart, dispStop, nLoopPerEntry, nLoopOffset;
+  int nLoop = 0, nData = 0;
+
+  LoopComputeParam(MugiqLoopParam *prm, ColorSpinorField *x)
+      : Nmom(prm->Nmom), FTSign(prm->FTSign), doMomProj(prm->doMomProj), doNonLocal(prm->doNonLocal),
+        nParity(x->SiteSubset()), volumeCB((int)x->VolumeCB()), calcType(prm->calcType) {
+    for (int i = 0; i < N_DIM_; i++) {
+      localL[i] = x->X(i);
+      totalL[i] = localL[i] * comm_dim(i);
+      locV4 *= localL[i];
+      if (i < N_DIM_ - 1) {
+        locV3 *= localL[i];
+        totV3 *= totalL[i];
+      }
+    }
+    locT = localL[N_DIM_ - 1];
+    totT = totalL[N_DIM_ - 1];
+    if (doMomProj) {
+      if (Nmom < 1 || (int)prm->momMatrix.size() != Nmom) errorQuda("Momentum matrix does not hold Nmom = %d momenta\n", Nmom);
+      momMatrix.assign((size_t)Nmom * momDim, 0);
+      for (int im = 0; im < Nmom; im++) {
+        if ((int)prm->momMatrix[im].size() != momDim) errorQuda("Momentum %d does not have %d components\n", im, momDim);
+        for (int id = 0; id < momDim; id++) momMatrix[MOM_MATRIX_IDX(id, im)] = prm->momMatrix[im][id];
+      }
+    }
+    if (doNonLocal) {
+      nDispEntries = (int)prm->disp_str.size();
+      if (nDispEntries != (int)prm->disp_start.size() || nDispEntries != (int)prm->disp_stop.size())
+        errorQuda("Displacement string length not compatible with displacement limits length\n");
+      int offset = 1;  // slot 0 is the ultra-local loop
+      for (int id = 0; id < nDispEntries; id++) {
+        int start = prm->disp_start[id], stop = prm->disp_stop[id];
+        if (start > stop) {
+          warningQuda("Stop length is smaller than Start length for displacement %d. Will switch lengths!\n", id);
+          std::swap(start, stop);
+        }
+        dispEntry.push_back(id < (int)prm->disp_entry.size() ? prm->disp_entry[id] : prm->disp_str[id]);
+        dispString.push_back(prm->disp_str[id]);
+        dispStart.push_back(start);
+        dispStop.push_back(stop);
+        nLoopPerEntry.push_back(stop - start + 1);
+        nLoopOffset.push_back(offset);
+        offset += stop - start + 1;
+      }
+      nLoop = offset;
+    } else {
+      nLoop = 1;
+    }
+    nData = nLoop * nG;
+    printfQuda("%s: Loop compute parameters are set\n", __func__);
+  }
+};
+
+template <typename Float, QudaFieldOrder fieldOrder>
+Loop_Mugiq<Float, fieldOrder>::Loop_Mugiq(MugiqLoopParam *loopParams_, Eigsolve_Mugiq *eigsolve_)
+    : cPrm(nullptr), displace(nullptr), eigsolve(eigsolve_), refVec(nullptr), nElemMomTotPerLoop(0), nElemMomLocPerLoop(0),
+      nElemPosLocPerLoop(0), nElemMomTot(0), nElemMomLoc(0), nElemPosLoc(0), nElemPhMat(0), MomProjDone(MUGIQ_BOOL_FALSE),
+      writeDataPos(loopParams_->writePosSpaceHDF5), writeDataMom(loopParams_->writeMomSpaceHDF5),
+      momSpaceFilename(loopParams_->fname_mom_h5), posSpaceFilename(loopParams_->fname_pos_h5) {
+  printfQuda("\n*************************************************\n");
+  printfQuda("%s: Creating Loop computation environment\n", __func__);
+  if (!eigsolve || eigsolve->eVecs.empty()) errorQuda("%s: no eigenvectors were given", __func__);
+  if (eigsolve->useMGenv && eigsolve->computeCoarse)
+    errorQuda("%s: coarse eigenvectors need QUDA's multigrid transfer, which is an external input of this build", __func__);
+  refVec = eigsolve->eVecs[0];
+  if (refVec->SiteSubset() != QUDA_FULL_SITE_SUBSET) errorQuda("%s: This class supports only Full Site Subset spinors!", __func__);
+  if (refVec->FieldOrder() != fieldOrder) errorQuda("%s: eigenvector field order %d does not match the template", __func__, (int)refVec->FieldOrder());
+
+  cPrm = new LoopComputeParam(loopParams_, refVec);
+  setupComms();
+  allocateDataMemory();
+  copyGammaToConstMem();
+  if (cPrm->doMomProj) createPhaseMatrix();
+  if (cPrm->doNonLocal) displace = new Displace<Float, fieldOrder>(loopParams_, refVec, refVec->Precision());
+  printLoopComputeParams();
+  printfQuda("*************************************************\n\n");
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> Loop_Mugiq<Float, fieldOrder>::~Loop_Mugiq() {
+  freeDataMemory();
+  if (displace) delete displace;
+  if (cPrm) delete cPrm;
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> int Loop_Mugiq<Float, fieldOrder>::nLoop() const { return cPrm->nLoop; }
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::setupComms() {
+  // one rank: it is its own "space" and "time" communicator
+  tCoord = comm_coord(3);
+  IamTimeProcess = MUGIQ_BOOL_TRUE;
+  commsAreSet = MUGIQ_BOOL_TRUE;
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::allocateDataMemory() {
+  nElemPosLocPerLoop = cPrm->nG * cPrm->locV4;
+  nElemMomLocPerLoop = (long long)cPrm->nG * cPrm->Nmom * cPrm->locT;
+  nElemMomTotPerLoop = (long long)cPrm->nG * cPrm->Nmom * cPrm->totT;
+  nElemPosLoc = nElemPosLocPerLoop * cPrm->nLoop;
+  nElemMomLoc = nElemMomLocPerLoop * cPrm->nLoop;
+  nElemMomTot = nElemMomTotPerLoop * cPrm->nLoop;
+  nElemPhMat = (long long)cPrm->Nmom * cPrm->locV3;
+
+  if (cPrm->doMomProj) {
+    dataMom_h = static_cast<complex<Float> *>(calloc(nElemMomLoc, SizeCplxFloat));
+    dataMom = static_cast<complex<Float> *>(calloc(nElemMomLoc, SizeCplxFloat));
+    dataMom_bcast = static_cast<complex<Float> *>(calloc(nElemMomTot, SizeCplxFloat));
+    if (!dataMom_h || !dataMom || !dataMom_bcast) errorQuda("%s: Could not allocate host momentum-space buffers\n", __func__);
+    HOST_CUDA(cudaMalloc((void **)&phaseMatrix_d, SizeCplxFloat * nElemPhMat));
+    HOST_CUDA(cudaMalloc((void **)&dataPosMP_d, SizeCplxFloat * nElemPosLoc));
+    HOST_CUDA(cudaMalloc((void **)&dataMom_d, SizeCplxFloat * nElemMomLoc));
+    const long long ws = mugiq_b200_momproj_workspace_bytes((long long)cPrm->locT * cPrm->nData, cPrm->Nmom, cPrm->locV3,
+                                                            (int)precision_of<Float>());
+    if (ws < 0) errorQuda("%s: %s", __func__, mugiq_b200_last_error());
+    HOST_CUDA(cudaMalloc(&momWorkspace_d, (size_t)ws));
+  }
+  HOST_CUDA(cudaMallocHost((void **)&dataPos, SizeCplxFloat * nElemPosLoc));  // pinned: the D2H copy of :512 runs at PCIe speed
+  HOST_CUDA(cudaMalloc((void **)&dataPos_d, SizeCplxFloat * nElemPosLoc));
+  HOST_CUDA(cudaMemset(dataPos_d, 0, SizeCplxFloat * nElemPosLoc));
+  printfQuda("%s: Data buffers allocated\n", __func__);
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::freeDataMemory() {
+  auto dfree = [](auto *&p) {
+    if (p) cudaFree((void *)p);
+    p = nullptr;
+  };
+  auto hfree = [](auto *&p) {
+    if (p) free((void *)p);
+    p = nullptr;
+  };
+  hfree(dataMom_h);
+  hfree(dataMom);
+  hfree(dataMom_bcast);
+  if (dataPos) cudaFreeHost(dataPos);
+  dataPos = nullptr;
+  dfree(dataPos_d);
+  dfree(dataPosMP_d);
+  dfree(dataMom_d);
+  dfree(phaseMatrix_d);
+  dfree(momWorkspace_d);
+  dfree(evecStage_d);
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::copyGammaToConstMem() {
+  copyGammaCoeffStructToSymbol<Float>();
+  copyGammaMapStructToSymbol<Float>();
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::createPhaseMatrix() {
+  createPhaseMatrixGPU<Float>(phaseMatrix_d, cPrm->momMatrix.data(), cPrm->locV3, cPrm->Nmom, (int)cPrm->FTSign, cPrm->localL,
+                              cPrm->totalL);
+  printfQuda("%s: Phase matrix created\n", __func__);
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::printLoopComputeParams() {
+  printfQuda("Loop computation: %d loop(s) = ultra-local + %d displacement entr%s, %d momenta, momentum projection %s\n",
+             cPrm->nLoop, cPrm->nDispEntries, cPrm->nDispEntries == 1 ? "y" : "ies", cPrm->Nmom, cPrm->doMomProj ? "on" : "off");
+  for (int id = 0; id < cPrm->nDispEntries; id++)
+    printfQuda("  entry %d: %s, lengths %d..%d, loops %d..%d\n", id, cPrm->dispString[id].c_str(), cPrm->dispStart[id],
+               cPrm->dispStop[id], cPrm->nLoopOffset[id], cPrm->nLoopOffset[id] + cPrm->nLoopPerEntry[id] - 1);
+  printfQuda("  local lattice %d %d %d %d, Fourier sign %d\n", cPrm->localL[0], cPrm->localL[1], cPrm->localL[2], cPrm->localL[3],
+             (int)cPrm->FTSign);
+}
+
+// The eigenvector x displacement loop nest (lib/loop_mugiq.cpp:440-525).
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::computeCoarseLoop() {
+  const int nEv = eigsolve->eigParams->nEv;
+  if (nEv < 1 || nEv > (int)eigsolve->eVecs.size()) errorQuda("%s: nEv = %d but %zu eigenvectors were given", __func__, nEv, eigsolve->eVecs.size());
+  if (!eigsolve->eVals_sigma || (int)eigsolve->eVals_sigma->size() < nEv)
+    errorQuda("%s: singular values are only defined for MdagM / MMdag eigensolves and are required here", __func__);
+  const QudaPrecision evecPrec = eigsolve->eVecs[0]->Precision();
+  if (evecPrec != precision_of<Float>()) errorQuda("%s: Precision not supported!", __func__);
+  const mugiq_b200_geom_t geom = make_geom(cPrm->localL, precision_of<Float>());
+
+  // entries in the order given; directions parsed exactly as Displace does for the hop-by-hop interface
+  std::vector<mugiq_b200_disp_entry_t> entries;
+  for (int id = 0; id < cPrm->nDispEntries; id++) {
+    displace->setupDisplacement(cPrm->dispString[id]);
+    entries.push_back({(int)displace->dispDir, (int)displace->dispSign, cPrm->dispStart[id], cPrm->dispStop[id]});
+  }
+  mugiq_b200_loop_plan_t *plan = nullptr;
+  if (displace) {
+    displace->createLoopPlan(entries);
+    plan = displace->plan;
+  } else {
+    MUGIQ_CHECK(mugiq_b200_loop_plan_create(&plan, nullptr, nullptr, 0, &geom, nullptr));
+  }
+  if (mugiq_b200_loop_plan_nloop(plan) != cPrm->nLoop) errorQuda("%s: plan holds %d loops, expected %d", __func__, mugiq_b200_loop_plan_nloop(plan), cPrm->nLoop);
+
+  // eigenvectors are consumed in batches; QUDA-native orders are converted to the site-major layout batch by batch
+  const int batch = 32;
+  const size_t fieldBytes = eigsolve->eVecs[0]->Bytes();
+  const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
+  if (native && !evecStage_d) HOST_CUDA(cudaMalloc(&evecStage_d, fieldBytes * batch));
+  std::vector<const void *> ptr(batch);
+  std::vector<double> sigma(batch);
+  for (int n0 = 0; n0 < nEv; n0 += batch) {
+    const int nb = std::min(batch, nEv - n0);
+    for (int i = 0; i < nb; i++) {
+      ColorSpinorField *v = eigsolve->eVecs[n0 + i];
+      sigma[i] = (double)(Float)(*(eigsolve->eVals_sigma))[n0 + i];
+      if (native) {
+        void *dst = static_cast<char *>(evecStage_d) + (size_t)i * fieldBytes;
+        MUGIQ_CHECK(mugiq_b200_ingest_spinor(dst, v->V(), abi_order(v->FieldOrder()), &geom, nullptr));
+        ptr[i] = dst;
+      } else {
+        ptr[i] = v->V();
+      }
+    }
+    MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0, nullptr));
+    printfQuda("%s: Loop trace for eigenvectors %04d - %04d completed\n", __func__, n0, n0 + nb - 1);
+  }
+  MUGIQ_CHECK(mugiq_b200_loop_plan_finalize(plan, dataPos_d, 0, nullptr));
+  if (!displace) mugiq_b200_loop_plan_destroy(plan);
+
+  // always copy the device position-space buffer to the host
+  HOST_CUDA(cudaMemcpy(dataPos, dataPos_d, SizeCplxFloat * nElemPosLoc, cudaMemcpyDeviceToHost));
+  HOST_CUDA(cudaDeviceSynchronize());
+  printfQuda("%s: Loop trace completed\n", __func__);
+
+  if (cPrm->doMomProj) {
+    performMomentumProjection();
+    printfQuda("%s: Momentum projection completed\n", __func__);
+  }
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::performMomentumProjection() {
+  if (MomProjDone) errorQuda("%s: Not supposed to be called more than once!!", __func__);
+  if (!commsAreSet) setupComms();
+  const long long locV3 = cPrm->locV3;
+  const int locT = cPrm->locT, Nmom = cPrm->Nmom, nLoop = cPrm->nLoop, nData = cPrm->nData;
+  if (nData != nLoop * N_GAMMA_) errorQuda("%s: This function assumes that nData = nLoop * NGamma\n", __func__);
+
+  // volume4d-inside-gamma-inside-nLoop -> time-inside-nData-inside-v3, with the Gamma -> g5*Gamma map
+  convertIdxOrder_mapGamma<Float>(dataPosMP_d, dataPos_d, nData, nLoop, cPrm->nParity, cPrm->volumeCB, cPrm->localL);
+  // dataMom(M x N) = dataPosMP(M x K) * phase(K x N), column-major
+  const long long M = (long long)locT * nData, K = locV3;
+  MUGIQ_CHECK(mugiq_b200_momproj(dataMom_d, dataPosMP_d, phaseMatrix_d, M, Nmom, K, (int)precision_of<Float>(), momWorkspace_d, nullptr));
+  HOST_CUDA(cudaMemcpy(dataMom_h, dataMom_d, SizeCplxFloat * nElemMomLoc, cudaMemcpyDeviceToHost));
+  // MPI_Reduce over the "space" ranks and MPI_Gather + MPI_Bcast over the "time" ranks: one rank each
+  memcpy(dataMom, dataMom_h, SizeCplxFloat * nElemMomLoc);
+  memcpy(dataMom_bcast, dataMom, SizeCplxFloat * nElemMomLoc);
+  MomProjDone = MUGIQ_BOOL_TRUE;
+}
+
+// HDF5 is not available in this build.  The same dataset tree the reference creates
+// (/mom_%+d_%+d_%+d/disp_0 | disp_<dir>_<len>/<GammaName>/loop, shape [T][2], lib/loop_mugiq.cpp:582-633) is written
+// as a flat file: a text index (one "dataset <path> <T> <offset>" line each) followed by the raw values.  Tags are
+// not truncated (the reference's group2_tag[10] collides disp_+z_10 with disp_+z_1).  mugiq_b200/h5lite.py reads it.
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::writeLoopsHDF5_Mom() {
+  if (!MomProjDone) errorQuda("%s: momentum projection has not been performed", __func__);
+  if (momSpaceFilename.empty()) errorQuda("%s: momentum-space file name is empty", __func__);
+  const int totT = cPrm->totT, nData = cPrm->nData;
+  std::vector<std::string> tags{"disp_0"};
+  for (int id = 0; id < cPrm->nDispEntries; id++)
+    for (int len = cPrm->dispStart[id]; len <= cPrm->dispStop[id]; len++) tags.push_back("disp_" + cPrm->dispString[id] + "_" + std::to_string(len));
+  std::string index = std::string("MUGIQ-B200 LOOPS v1 dtype ") + (sizeof(Float) == 8 ? "f64" : "f32") + "\n";
+  std::vector<Float> payload;
+  payload.reserve((size_t)2 * nElemMomTot);
+  for (int im = 0; im < cPrm->Nmom; im++) {
+    char momTag[64];
+    snprintf(momTag, sizeof(momTag), "mom_%+d_%+d_%+d", cPrm->momMatrix[MOM_MATRIX_IDX(0, im)], cPrm->momMatrix[MOM_MATRIX_IDX(1, im)],
+             cPrm->momMatrix[MOM_MATRIX_IDX(2, im)]);
+    for (int iL = 0; iL < cPrm->nLoop; iL++)
+      for (int ig = 0; ig < N_GAMMA_; ig++) {
+        index += "dataset /" + std::string(momTag) + "/" + tags[iL] + "/" + GammaName()[ig] + "/loop " + std::to_string(totT) + " " +
+                 std::to_string(payload.size() * sizeof(Float)) + "\n";
+        const complex<Float> *src = dataMom_bcast + (size_t)totT * ig + (size_t)totT * N_GAMMA_ * iL + (size_t)totT * nData * im;
+        for (int t = 0; t < totT; t++) {
+          payload.push_back(src[t].real());
+          payload.push_back(src[t].imag());
+        }
+      }
+  }
+  index += "end\n";
+  std::ofstream out(momSpaceFilename, std::ios::binary);
+  if (!out) errorQuda("%s: cannot open %s for writing", __func__, momSpaceFilename.c_str());
+  out.write(index.data(), (std::streamsize)index.size());
+  out.write(reinterpret_cast<const char *>(payload.data()), (std::streamsize)(payload.size() * sizeof(Float)));
+  printfQuda("%s: Momentum-space loops written to %s\n", __func__, momSpaceFilename.c_str());
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::writeLoopsHDF5_Pos() {
+  errorQuda("%s: Not supported yet!\n", __func__);  // as in the reference (lib/loop_mugiq.cpp:661-663)
+}
+
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::writeLoopsHDF5() {
+  if (cPrm->doMomProj) {
+    if (writeDataMom) {
+      printfQuda("%s: Will write the momentum-space loop data\n", __func__);
+    } else {
+      warningQuda("%s: Performed momentum projection, but got writeDatMom = FALSE.\n", __func__);
+      warningQuda("%s: Will proceed to write momentum-space loop data\n", __func__);
+      writeDataMom = MUGIQ_BOOL_TRUE;
+    }
+    writeLoopsHDF5_Mom();
+  } else if (!writeDataPos) {
+    warningQuda("%s: Did not perform momentum projection, but got writeDatPos = FALSE.\n", __func__);
+    warningQuda("%s: Will proceed to write position-space loop data\n", __func__);
+    writeDataPos = MUGIQ_BOOL_TRUE;
+  }
+  if (writeDataPos) {
+    printfQuda("%s: Will write the position-space loop data\n", __func__);
+    writeLoopsHDF5_Pos();
+  }
+}
+
+template class Loop_Mugiq<float, QUDA_FLOAT2_FIELD_ORDER>;
+template class Loop_Mugiq<float, QUDA_FLOAT4_FIELD_ORDER>;
+template class Loop_Mugiq<float, QUDA_SPACE_SPIN_COLOR_FIELD_ORDER>;
+template class Loop_Mugiq<double, QUDA_FLOAT2_FIELD_ORDER>;
+template class Loop_Mugiq<double, QUDA_FLOAT4_FIELD_ORDER>;
+template class Loop_Mugiq<double, QUDA_SPACE_SPIN_COLOR_FIELD_ORDER>;

@@ -1,0 +1,161 @@
+// loop_driver.cpp — stand-in for the reference's `loop` executable (/root/reference/tests/loop.cpp:751-961) on top of
+// the host mirror: same loop-related options (tests/test_params_mugiq.cpp:77-112), but eigenpairs and links are read
+// from raw files (QUDA's eigensolver and gauge I/O are external inputs) instead of being computed / loaded by QUDA.
+//
+//   loop_driver --dim 4 4 4 8 --prec double --n-ev 16 --evecs-file ev.bin --sigma-file sig.bin --gauge-file u.bin
+//               --loop-do-nonlocal yes --displace-entry-string "+z:1,3;-x:2" --loop-do-momproj yes
+//               --momenta-filename mom.txt --loop-ft-sign minus --loop-write-mom-space yes
+//               --loop-mom-space-filename loops.dat [--field-order site|float2|float4] [--dump-pos f] [--dump-mom f]
+//   loop_driver --parse-only ...   parses and prints the loop parameters, touches no GPU (used by the CPU tests)
+// File formats: evecs [nEv][V4 (even/odd order)][12] complex, gauge [4][V4][3][3] complex, sigma nEv doubles.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+
+#include "host_util.h"
+#include "loop_mugiq.h"
+
+using namespace quda;
+
+static std::vector<char> slurp(const std::string &f, size_t expect) {
+  std::ifstream in(f, std::ios::binary);
+  if (!in) errorQuda("cannot open %s", f.c_str());
+  std::vector<char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  if (expect && buf.size() != expect) errorQuda("%s holds %zu bytes, expected %zu", f.c_str(), buf.size(), expect);
+  return buf;
+}
+static bool yes(const std::string &s) { return s == "yes" || s == "true" || s == "1"; }
+
+// site-major host field -> QUDA native order (for exercising the FLOAT2 / FLOAT4 ingest path)
+template <typename Float> static void to_native(std::vector<char> &field, QudaFieldOrder order, size_t volumeCB) {
+  if (order == QUDA_SPACE_SPIN_COLOR_FIELD_ORDER) return;
+  const Float *src = reinterpret_cast<const Float *>(field.data());
+  std::vector<char> out(field.size());
+  Float *dst = reinterpret_cast<Float *>(out.data());
+  const int N = order == QUDA_FLOAT2_FIELD_ORDER ? 2 : 4;
+  for (int pty = 0; pty < 2; pty++)
+    for (size_t x = 0; x < volumeCB; x++)
+      for (int k = 0; k < 24; k++)
+        dst[pty * volumeCB * 24 + ((size_t)(k / N) * volumeCB + x) * N + k % N] = src[(pty * volumeCB + x) * 24 + k];
+  field.swap(out);
+}
+
+template <typename Float> static int run(std::map<std::string, std::string> &opt, const int X[4], MugiqLoopParam &prm, int nEv,
+                                         QudaFieldOrder order) {
+  const size_t V4 = (size_t)X[0] * X[1] * X[2] * X[3];
+  const QudaPrecision prec = precision_of<Float>();
+  const size_t fieldBytes = V4 * 24 * sizeof(Float);
+  std::vector<char> ev = slurp(opt["--evecs-file"], fieldBytes * nEv);
+  std::vector<char> sg = slurp(opt["--sigma-file"], sizeof(double) * nEv);
+  std::vector<double> sigma(nEv);
+  memcpy(sigma.data(), sg.data(), sg.size());
+  std::vector<char> gauge;
+  QudaGaugeParam gp;
+  if (prm.doNonLocal) {
+    gauge = slurp(opt["--gauge-file"], 4 * V4 * 18 * sizeof(Float));
+    for (int i = 0; i < 4; i++) {
+      gp.X[i] = X[i];
+      prm.gauge[i] = gauge.data() + (size_t)i * V4 * 18 * sizeof(Float);
+    }
+    gp.cpu_prec = gp.cuda_prec = prec;
+    gp.gauge_order = QUDA_QDP_GAUGE_ORDER;
+    prm.gauge_param = &gp;
+  }
+  std::vector<ColorSpinorField *> fields;
+  ColorSpinorParam cs;
+  for (int i = 0; i < 4; i++) cs.x[i] = X[i];
+  cs.precision = prec;
+  cs.fieldOrder = order;
+  for (int n = 0; n < nEv; n++) {
+    std::vector<char> one(ev.begin() + n * fieldBytes, ev.begin() + (n + 1) * fieldBytes);
+    to_native<Float>(one, order, V4 / 2);
+    fields.push_back(ColorSpinorField::Create(cs));
+    HOST_CUDA(cudaMemcpy(fields.back()->V(), one.data(), fieldBytes, cudaMemcpyHostToDevice));
+  }
+  QudaEigParam qe;
+  qe.nEv = nEv;
+  MugiqEigParam ep(&qe);
+  Eigsolve_Mugiq eigsolve(&ep, fields, sigma);
+
+  if (opt.count("--dump-pos") || opt.count("--dump-mom")) {
+    // class-level use (what computeLoop<Float,order> does), keeping the object to read its buffers
+    auto dump = [&](auto *loop) {
+      loop->computeCoarseLoop();
+      if (prm.writeMomSpaceHDF5 || prm.writePosSpaceHDF5) loop->writeLoopsHDF5();
+      if (opt.count("--dump-pos")) std::ofstream(opt["--dump-pos"], std::ios::binary).write((const char *)loop->hostDataPos(), loop->numElemPos() * 2 * sizeof(Float));
+      if (opt.count("--dump-mom") && prm.doMomProj) std::ofstream(opt["--dump-mom"], std::ios::binary).write((const char *)loop->hostDataMom(), loop->numElemMom() * 2 * sizeof(Float));
+      delete loop;
+    };
+    if (order == QUDA_FLOAT2_FIELD_ORDER) dump(new Loop_Mugiq<Float, QUDA_FLOAT2_FIELD_ORDER>(&prm, &eigsolve));
+    else if (order == QUDA_FLOAT4_FIELD_ORDER) dump(new Loop_Mugiq<Float, QUDA_FLOAT4_FIELD_ORDER>(&prm, &eigsolve));
+    else dump(new Loop_Mugiq<Float, QUDA_SPACE_SPIN_COLOR_FIELD_ORDER>(&prm, &eigsolve));
+  } else {
+    setExternalEigsolve(&eigsolve);
+    QudaMultigridParam mg;
+    mg.n_level = 0;
+    computeLoop<Float>(mg, qe, prm, MUGIQ_BOOL_FALSE, MUGIQ_BOOL_FALSE);
+    setExternalEigsolve(nullptr);
+  }
+  for (ColorSpinorField *f : fields) delete f;
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> opt;
+  int X[4] = {0, 0, 0, 0};
+  bool parseOnly = false;
+  for (int i = 1; i < argc; i++) {
+    const std::string a = argv[i];
+    if (a == "--parse-only") {
+      parseOnly = true;
+    } else if (a == "--dim") {
+      if (i + 4 >= argc) errorQuda("--dim needs four extents");
+      for (int d = 0; d < 4; d++) X[d] = atoi(argv[++i]);
+    } else if (a.rfind("--", 0) == 0) {
+      if (i + 1 >= argc) errorQuda("option %s needs a value", a.c_str());
+      opt[a] = argv[++i];
+    } else {
+      errorQuda("unexpected argument %s", a.c_str());
+    }
+  }
+  if (opt.count("--verbosity") && opt["--verbosity"] == "verbose") setVerbosityQuda(QUDA_VERBOSE);
+  MugiqLoopParam prm;
+  if (opt.count("--loop-do-nonlocal") && yes(opt["--loop-do-nonlocal"])) parseDisplaceEntryString(prm, opt["--displace-entry-string"]);
+  if (opt.count("--loop-do-momproj") && yes(opt["--loop-do-momproj"])) {
+    if (!opt.count("--momenta-filename")) errorQuda("Got option '--loop-do-momproj yes' but option --momenta-filename is not set!\n");
+    readMomentaFile(prm, opt["--momenta-filename"]);
+  }
+  if (opt.count("--loop-ft-sign")) {
+    const std::string s = opt["--loop-ft-sign"];
+    if (s == "plus") prm.FTSign = LOOP_FT_SIGN_PLUS;
+    else if (s == "minus") prm.FTSign = LOOP_FT_SIGN_MINUS;
+    else errorQuda("Unknown --loop-ft-sign %s (plus/minus)", s.c_str());
+  }
+  if (opt.count("--loop-write-mom-space")) prm.writeMomSpaceHDF5 = yes(opt["--loop-write-mom-space"]) ? MUGIQ_BOOL_TRUE : MUGIQ_BOOL_FALSE;
+  if (opt.count("--loop-write-pos-space")) prm.writePosSpaceHDF5 = yes(opt["--loop-write-pos-space"]) ? MUGIQ_BOOL_TRUE : MUGIQ_BOOL_FALSE;
+  if (opt.count("--loop-mom-space-filename")) prm.fname_mom_h5 = opt["--loop-mom-space-filename"];
+  if (opt.count("--loop-pos-space-filename")) prm.fname_pos_h5 = opt["--loop-pos-space-filename"];
+  if (parseOnly) {
+    printf("nonlocal %d entries %zu\n", (int)prm.doNonLocal, prm.disp_str.size());
+    for (size_t i = 0; i < prm.disp_str.size(); i++) printf("entry %zu %s %d %d\n", i, prm.disp_str[i].c_str(), prm.disp_start[i], prm.disp_stop[i]);
+    printf("momproj %d Nmom %d ftsign %d\n", (int)prm.doMomProj, prm.Nmom, (int)prm.FTSign);
+    for (auto &p : prm.momMatrix) printf("mom %d %d %d\n", p[0], p[1], p[2]);
+    return 0;
+  }
+  const int nEv = opt.count("--n-ev") ? atoi(opt["--n-ev"].c_str()) : 0;
+  if (nEv < 1) errorQuda("--n-ev must be positive");
+  QudaFieldOrder order = QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
+  if (opt.count("--field-order")) {
+    if (opt["--field-order"] == "float2") order = QUDA_FLOAT2_FIELD_ORDER;
+    else if (opt["--field-order"] == "float4") order = QUDA_FLOAT4_FIELD_ORDER;
+    else if (opt["--field-order"] != "site") errorQuda("Unknown --field-order %s", opt["--field-order"].c_str());
+  }
+  const std::string prec = opt.count("--prec") ? opt["--prec"] : "double";
+  if (prec == "double") return run<double>(opt, X, prm, nEv, order);
+  if (prec == "single") return run<float>(opt, X, prm, nEv, order);
+  errorQuda("Unknown --prec %s (double/single)", prec.c_str());
+  return 1;
+}

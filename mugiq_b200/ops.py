@@ -245,9 +245,9 @@ def prof_report():
     out = {}
     for k in range(lib.mugiq_b200_prof_num_kernels()):
         n, t = C.c_longlong(), C.c_longlong()
-        ms, b = C.c_double(), C.c_double()
-        check(lib.mugiq_b200_prof_query(k, C.byref(n), C.byref(t), C.byref(ms), C.byref(b)))
+        ms, b, f = C.c_double(), C.c_double(), C.c_double()
+        check(lib.mugiq_b200_prof_query(k, C.byref(n), C.byref(t), C.byref(ms), C.byref(b), C.byref(f)))
         if n.value:
             out[lib.mugiq_b200_prof_name(k).decode()] = {"launches": n.value, "timed": t.value, "ms": ms.value,
-                                                         "alg_bytes": b.value}
+                                                         "alg_bytes": b.value, "alg_flops": f.value}
     return out

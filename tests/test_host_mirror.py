@@ -1,0 +1,133 @@
+"""The C++ host-side mirror of the reference interface (mugiq_b200/host: Loop_Mugiq, Displace, computeLoop, the wrapper
+functions and the loop_driver executable standing in for the reference's tests/loop.cpp).  CPU part: it builds, links
+against the C-ABI library, parses the reference's option grammar and aborts like errorQuda on bad input.  GPU part:
+the driver's results equal the oracle's for site-major, FLOAT2 and FLOAT4 eigenvector orders."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_err, TOL_F64, TOL_F32
+
+HOST = os.path.join(ROOT, "mugiq_b200", "host")
+DRIVER = os.path.join(HOST, "build", "loop_driver")
+
+
+@pytest.fixture(scope="module")
+def driver():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "mugiq_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    assert os.path.exists(DRIVER)
+    return DRIVER
+
+
+def run(driver, *args):
+    return subprocess.run([driver, *[str(a) for a in args]], capture_output=True, text=True)
+
+
+def test_host_library_exports_reference_interface(driver):
+    out = subprocess.run(["nm", "-DC", os.path.join(ROOT, "mugiq_b200", "lib", "libmugiq_host.so")], capture_output=True,
+                         text=True).stdout
+    for sym in ["Loop_Mugiq<double, (QudaFieldOrder_s)2>::computeCoarseLoop()",
+                "Loop_Mugiq<float, (QudaFieldOrder_s)4>::writeLoopsHDF5()",
+                "Displace<double, (QudaFieldOrder_s)2>::Displace(MugiqLoopParam_s*, quda::ColorSpinorField*, QudaPrecision_s)",
+                "void computeLoop<double>(QudaMultigridParam_s, QudaEigParam_s, MugiqLoopParam_s, MuGiqBool_s, MuGiqBool_s)",
+                "void performLoopContraction<double, (QudaFieldOrder_s)2>(std::complex<double>*, quda::ColorSpinorField*, "
+                "quda::ColorSpinorField*, double)",
+                "void convertIdxOrder_mapGamma<float>(std::complex<float>*, std::complex<float> const*, int, int, int, int, "
+                "int const*)",
+                "void createPhaseMatrixGPU<double>(std::complex<double>*, int const*, long long, int, int, int const*, int const*)",
+                "void performCovariantDisplacementVector<double, (QudaFieldOrder_s)4>"]:
+        assert sym in out, sym
+
+
+def test_driver_parses_reference_option_grammar(driver, tmp_path):
+    mom = tmp_path / "mom.txt"
+    mom.write_text("0 0 0\n1 0 0\n\n0 -1 1\n")
+    r = run(driver, "--parse-only", "--loop-do-nonlocal", "yes", "--displace-entry-string", "+z:1,8;-x:3;+t:5,2",
+            "--loop-do-momproj", "yes", "--momenta-filename", mom, "--loop-ft-sign", "plus")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "nonlocal 1 entries 3"
+    assert lines[1:4] == ["entry 0 +z 1 8", "entry 1 -x 3 3", "entry 2 +t 5 2"]
+    assert "momproj 1 Nmom 3 ftsign 1" in lines
+    assert lines[-1] == "mom 0 -1 1"
+
+
+@pytest.mark.parametrize("entry,msg", [("+z:1:8", "Wrong format"), ("+z:1,2,3", "Wrong format"), ("+z:a", "Wrong format"),
+                                       ("", "--displace-entry-string is not set")])
+def test_driver_aborts_like_errorQuda(driver, entry, msg):
+    r = run(driver, "--parse-only", "--loop-do-nonlocal", "yes", "--displace-entry-string", entry)
+    assert r.returncode != 0 and msg in r.stderr
+
+
+def test_driver_rejects_bad_momenta_file(driver, tmp_path):
+    mom = tmp_path / "mom.txt"
+    mom.write_text("0 0 0\n1 x 0\n")
+    r = run(driver, "--parse-only", "--loop-do-momproj", "yes", "--momenta-filename", mom)
+    assert r.returncode != 0 and "Incorrect file format in Line 1" in r.stderr
+
+
+def _inputs(tmp_path, L, nEv, prec):
+    from mugiq_b200 import synth
+    cdt = np.complex128 if prec == "double" else np.complex64
+    ev = synth.random_evecs_np(L, nEv, seed=51).astype(cdt)
+    U = synth.random_gauge(L, seed=51).astype(cdt)
+    sig = synth.sigmas(nEv)
+    ev.tofile(tmp_path / "ev.bin")
+    U.tofile(tmp_path / "u.bin")
+    sig.tofile(tmp_path / "sig.bin")
+    return ev, U, sig
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["site", "float2", "float4"])
+@pytest.mark.parametrize("prec", ["double", "single"])
+def test_driver_matches_oracle(driver, oracle, tmp_path, order, prec):
+    from oracle import numpy_check as npc
+    from mugiq_b200.h5lite import read_loops_file
+    from mugiq_b200.params import momenta_up_to, GAMMA_NAMES
+    L, nEv = (4, 4, 4, 8), 6
+    ev, U, sig = _inputs(tmp_path, L, nEv, prec)
+    mom = momenta_up_to(1)
+    (tmp_path / "mom.txt").write_text("".join(f"{p[0]} {p[1]} {p[2]}\n" for p in mom))
+    entries = [(2, 1, 1, 3), (0, 0, 2, 2), (3, 0, 1, 1), (3, 1, 1, 1)]
+    r = run(driver, "--dim", *L, "--prec", prec, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file",
+            tmp_path / "sig.bin", "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string",
+            "+z:1,3;-x:2;-t:1;+t:1", "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--loop-ft-sign",
+            "minus", "--loop-write-mom-space", "yes", "--loop-mom-space-filename", tmp_path / "loops.dat", "--field-order", order,
+            "--dump-pos", tmp_path / "pos.bin", "--dump-mom", tmp_path / "mom.bin")
+    assert r.returncode == 0, r.stderr
+    cdt = np.complex128 if prec == "double" else np.complex64
+    tol = TOL_F64 if prec == "double" else TOL_F32
+    ref = oracle.compute_loop(ev.astype(np.complex128), sig, U.astype(np.complex128), entries, L)
+    pos = np.fromfile(tmp_path / "pos.bin", dtype=cdt).reshape(ref.shape)
+    assert rel_err(pos, ref) < tol
+    ref_mom = npc.momentum_projection(ref, mom, -1, L)
+    dm = np.fromfile(tmp_path / "mom.bin", dtype=cdt).reshape(ref_mom.shape)
+    assert rel_err(dm, ref_mom) < tol
+    loops = read_loops_file(tmp_path / "loops.dat")
+    assert len(loops) == len(mom) * ref.shape[0] * 16
+    im = mom.index([0, 1, 0])
+    got = loops["/mom_+0_+1_+0/disp_+z_3/" + GAMMA_NAMES[7] + "/loop"]
+    assert np.abs(got - ref_mom[im, 7 + 16 * 3, :]).max() < tol * np.abs(ref_mom).max()
+
+
+@pytest.mark.gpu
+def test_driver_public_entry_point_and_fatal_errors(driver, tmp_path):
+    """computeLoop<Float>() through the registry (no dumps), then the reference's fatal paths: position-space writing is
+    'Not supported yet', a precision mismatch aborts."""
+    L, nEv = (4, 4, 4, 4), 3
+    _inputs(tmp_path, L, nEv, "double")
+    base = ["--dim", *L, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file", tmp_path / "sig.bin", "--gauge-file",
+            tmp_path / "u.bin"]
+    (tmp_path / "mom.txt").write_text("0 0 0\n")
+    r = run(driver, *base, "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--loop-write-mom-space", "yes",
+            "--loop-mom-space-filename", tmp_path / "l.dat")
+    assert r.returncode == 0, r.stderr
+    assert os.path.getsize(tmp_path / "l.dat") > 16 * 4 * 16
+    r = run(driver, *base, "--loop-write-pos-space", "yes")
+    assert r.returncode != 0 and "Not supported yet" in r.stderr
+    r = run(driver, *base, "--prec", "single")
+    assert r.returncode != 0  # evecs file has double-precision size
