@@ -155,6 +155,8 @@ def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from oracle import oracle as orc
+    orc.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     nev_s = cpu_sample_size(wl, min(15.0, 150.0 / (args.steps + 1)))
     times = []
     rate = threads = None
@@ -317,6 +319,8 @@ def run_ours(args, wl, name):
     # ---- cpu baseline (rank 0, N == 1 only) ---------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
         nev_s = cpu_sample_size(wl, 12.0)
         rate, threads, dt = cpu_loop_rate(wl, nev_s)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",

@@ -86,6 +86,15 @@ template <typename F> __device__ __forceinline__ void cmac(Cplx<F> &acc, const C
   acc.im = fma(a.re, b.im, acc.im);
   acc.im = fma(a.im, b.re, acc.im);
 }
+// a * b
+template <typename F> __device__ __forceinline__ Cplx<F> cmul(const Cplx<F> a, const Cplx<F> b) {
+  Cplx<F> r;
+  r.re = a.re * b.re;
+  r.re = fma(-a.im, b.im, r.re);
+  r.im = a.re * b.im;
+  r.im = fma(a.im, b.re, r.im);
+  return r;
+}
 // acc += conj(a) * b
 template <typename F> __device__ __forceinline__ void cmac_conj(Cplx<F> &acc, const Cplx<F> a, const Cplx<F> b) {
   acc.re = fma(a.re, b.re, acc.re);

@@ -14,7 +14,9 @@
 // Design ("kernels"; the numbers quoted are measured on B200, profiles/):
 //  * The kernel is FP64-FMA bound (B200: 34 TFLOP/s measured, DMMA shares the pipe): 360 DFMA/DMUL per
 //    (eigvec, site, displaced loop) + ~30 for the share of the ultra-local matrix, against 192 B of compulsory
-//    HBM traffic per (eigvec, site).  Everything else is arranged so that the FP64 pipe is the only busy unit.
+//    HBM traffic per (eigvec, site).  Everything else is arranged so that the FP64 pipe is the only busy unit:
+//    on this chip every other instruction takes FP64 issue slots (one IMAD per DFMA halves the DFMA rate,
+//    tools/microbench.cu), so the loop body is ~390 FP64 + ~175 other instructions per eigenvector.
 //  * CTA tile = NR (<= 4) lattice rows (all x at fixed y,z,t), preferably consecutive in y: in the even/odd
 //    site-major layout a row is two contiguous half-rows (one per parity) of Lx/2 sites x 192 B and consecutive-y
 //    rows are contiguous, so the tile and its shifted copies are fetched with a handful of multi-KB bulk-TMA
@@ -145,7 +147,6 @@ template <typename F> struct FusedArgs {
   F *dataPos;
   long long ul_off;    // complex offset of the ultra-local loop's block in dataPos, < 0: not in this launch
   int accumulate;
-  int dbg;             // experiments only: bit 0 = no arithmetic, bit 1 = no loads (MUGIQ_B200_FUSED_DBG)
 };
 
 constexpr int kSmemHeader = 2048;  // barriers + slot table
@@ -208,101 +209,167 @@ template <typename F> struct ThreadCtx {
 //             with one loop body in the instruction cache instead of four (no_instruction stalls were 12%).
 enum { UL_NONE = 0, UL_ALL = 1, UL_ROT = 2 };
 
+// ---- hot-loop primitives on 32-bit shared addresses.  On B200 every non-FP64 instruction costs FP64 issue slots
+// (tools/microbench.cu: one IMAD per DFMA drops the DFMA rate from 33.5 to 18.3 TFLOP/s at 8 warps per SM), so the loop
+// body avoids branches (predicated mbarrier / TMA instructions instead of `if (lane == 0)` blocks), address
+// arithmetic (running per-thread addresses, immediates for the colour offset) and integer division.
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, int pred) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(bar), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_if(uint32_t bar, uint32_t bytes, int pred) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}" ::"r"(bar),
+               "r"(bytes), "r"(pred)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_if(uint32_t dst, const void *src_gmem, uint32_t bytes, uint32_t bar, int pred) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}" ::"r"(dst),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "r"(pred)
+      : "memory");
+}
 // The eigenvector loop of one role: ND displaced loops in the group, this thread works on one of them and on its
 // share of the ultra-local entries.
 template <typename F, int ND, int UL>
 __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx<F> &c, const Cplx<F> (&W)[3][3],
                                           Cplx<F> (&M)[4][4], F (&Md)[4], Cplx<F> (&Mo)[6], const bool opposite) {
-  constexpr int kC = 2 * (int)sizeof(F);
-  const int dbg = A.dbg;
-  // producer side: copies c.warp, c.warp + nActive, ... of every stage
+  // producer side: this warp issues copies c.warp, c.warp + nActive, ... of every stage.  With the preferred tile
+  // (4 consecutive-y rows) a stage is 6-8 copies, i.e. at most one per warp: its descriptor lives in registers.
   uint32_t my_tx = 0;
   for (int i = c.warp; i < c.st->ncopies; i += c.nActive) my_tx += (uint32_t)c.st->cp_bytes[i];
-  int ps = 0;        // stage of the next eigenvector to issue
-  uint32_t pph = 1;  // parity to wait for on empty[ps]; toggles per pass over the ring, the first pass does not wait
-  auto issue_share = [&](int m) {
-    if (m >= c.S) mbar_wait(&c.empty[ps], pph);
-    if (c.lane == 0) {
-      mbar_expect_tx(&c.full[ps], my_tx);
-      const char *ev = static_cast<const char *>(A.vt.evec[m]);
-      char *dst = const_cast<char *>(c.stages) + (size_t)ps * c.stage_bytes;
-      for (int i = c.warp; i < c.st->ncopies; i += c.nActive)
-        tma_bulk_g2s(dst + c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4), (uint32_t)c.st->cp_bytes[i],
-                     &c.full[ps]);
-    }
-    __syncwarp();
-    if (++ps == c.S) {
-      ps = 0;
-      pph ^= 1u;
+  const bool has_copy = c.warp < c.st->ncopies;
+  const bool more_copies = c.warp + c.nActive < c.st->ncopies;
+  const uint32_t cp0_s = has_copy ? (uint32_t)c.st->cp_soff[c.warp] : 0u;
+  const uint32_t cp0_b = has_copy ? (uint32_t)c.st->cp_bytes[c.warp] : 0u;
+  const size_t cp0_g = has_copy ? ((size_t)c.st->cp_goff16[c.warp] << 4) : 0;
+  const int lead = c.lane == 0;
+  const uint32_t stages_u32 = smem_u32(c.stages);
+  const uint32_t full_u32 = smem_u32(c.full), empty_u32 = smem_u32(c.empty);
+  const int ring_bytes = c.S * c.stage_bytes;
+  constexpr int kC = 2 * (int)sizeof(F);
+
+  uint32_t p_full = full_u32, p_empty = empty_u32, p_dst = stages_u32;  // producer cursor (stage of the next issue)
+  int p_left = c.S;                                                      // stages until the cursor wraps
+  uint32_t p_par = 1;  // parity to wait for on the empty barrier; the first pass over the ring does not wait
+  auto issue_share = [&](int m, bool wait) {
+    if (wait) mbar_wait_u32(p_empty, p_par);
+    const char *ev = static_cast<const char *>(A.vt.evec[m]);
+    mbar_expect_tx_if(p_full, my_tx, lead);
+    tma_bulk_g2s_if(p_dst + cp0_s, ev + cp0_g, cp0_b, p_full, lead && has_copy);
+    if (more_copies)
+      for (int i = c.warp + c.nActive; i < c.st->ncopies; i += c.nActive)
+        tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4), (uint32_t)c.st->cp_bytes[i],
+                        p_full, lead);
+    p_full += 8;
+    p_empty += 8;
+    p_dst += (uint32_t)c.stage_bytes;
+    if (--p_left == 0) {
+      p_left = c.S;
+      p_full = full_u32;
+      p_empty = empty_u32;
+      p_dst = stages_u32;
+      p_par ^= 1u;
     }
   };
-  if (!(dbg & 2))
-    for (int m = 0; m < c.ahead && m < c.nvec; m++) issue_share(m);
+  for (int m = 0; m < c.ahead && m < c.nvec; m++) issue_share(m, false);  // ahead < S: no tenant to wait for
 
-  int s = 0;
-  uint32_t ph = 0;
+  // consumer cursor: absolute shared addresses of the 4 rotated spin blocks of v(x) and v(x+d) in the current stage
+  const char *a_own[4], *a_nbr[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    a_own[b] = c.stages + c.own_sp[b];
+    a_nbr[b] = c.stages + c.nbr_sp[b];
+  }
+  uint32_t c_full = full_u32, c_empty = empty_u32;
+  int c_left = c.S;
+  uint32_t c_par = 0;
+  const int n_issue = c.nvec - c.ahead;  // iterations that still have a stage to issue
   for (int n = 0; n < c.nvec; n++) {
-    if (n + c.ahead < c.nvec && !(dbg & 2)) issue_share(n + c.ahead);
-    if (!(dbg & 2)) mbar_wait(&c.full[s], ph);
-    const char *base = c.stages + (size_t)s * c.stage_bytes;
-    if (dbg & 1) {
-      __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.empty[s]);
-    } else {
-      const F is = (F)A.vt.inv_sigma[n];
-      Cplx<F> vp[12];
-      if (ND > 0) {
+    if (n < n_issue) issue_share(n + c.ahead, n + c.ahead >= c.S);
+    mbar_wait_u32(c_full, c_par);
+    const F is = (F)A.vt.inv_sigma[n];
+    Cplx<F> vp[12];
+    if (ND > 0) {
 #pragma unroll
-        for (int al = 0; al < 4; al++)
-#pragma unroll
-          for (int cp = 0; cp < 3; cp++) vp[al * 3 + cp] = lds_c<F>(base + c.nbr_sp[al] + cp * kC);
-      }
-#pragma unroll
-      for (int cc = 0; cc < 3; cc++) {
-        Cplx<F> lc[4];
-#pragma unroll
-        for (int be = 0; be < 4; be++) lc[be] = lds_c<F>(base + c.own_sp[be] + cc * kC);
-        if (cc == 2) {  // last shared-memory read of this stage: hand it back before the remaining FMAs
-          __syncwarp();
-          if (c.lane == 0) mbar_arrive(&c.empty[s]);
-        }
-        // (1/sigma) v(x): one scaling serves the displaced and the ultra-local accumulation
-        Cplx<F> ls[4];
-#pragma unroll
-        for (int be = 0; be < 4; be++) ls[be] = make_c<F>(lc[be].re * is, lc[be].im * is);
-        if (ND > 0) {
-          Cplx<F> Rc[4];
-#pragma unroll
-          for (int al = 0; al < 4; al++) {
-            Rc[al] = make_c<F>(0, 0);
-#pragma unroll
-            for (int cp = 0; cp < 3; cp++) cmac(Rc[al], W[cc][cp], vp[al * 3 + cp]);
-          }
-#pragma unroll
-          for (int be = 0; be < 4; be++)
-#pragma unroll
-            for (int al = 0; al < 4; al++) cmac_conj(M[be][al], ls[be], Rc[al]);
-        }
-        if (UL == UL_ALL) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            Md[k] = fma(ls[k].re, lc[k].re, Md[k]);
-            Md[k] = fma(ls[k].im, lc[k].im, Md[k]);
-          }
-#pragma unroll
-          for (int k = 4; k < 10; k++) cmac_conj(Mo[k - 4], ls[ul_pair_be(k)], lc[ul_pair_al(k)]);
-        }
-        if (UL == UL_ROT) {
-          Md[0] = fma(ls[0].re, lc[0].re, Md[0]);
-          Md[0] = fma(ls[0].im, lc[0].im, Md[0]);
-          cmac_conj(Mo[0], ls[0], lc[1]);
-          if (opposite) cmac_conj(Mo[1], ls[0], lc[2]);  // warp-uniform
-        }
+      for (int al = 0; al < 4; al++) {
+        vp[al * 3 + 0] = lds_c<F>(a_nbr[al]);
+        vp[al * 3 + 1] = lds_c<F>(a_nbr[al] + kC);
+        vp[al * 3 + 2] = lds_c<F>(a_nbr[al] + 2 * kC);
       }
     }
-    if (++s == c.S) {
-      s = 0;
-      ph ^= 1u;
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+      Cplx<F> lc[4];
+#pragma unroll
+      for (int be = 0; be < 4; be++) lc[be] = lds_c<F>(a_own[be] + cc * kC);
+      if (cc == 2) {  // last shared-memory read of this stage: hand it back before the remaining FMAs
+        __syncwarp();
+        mbar_arrive_if(c_empty, lead);
+      }
+      // (1/sigma) v(x): one scaling serves the displaced and the ultra-local accumulation
+      Cplx<F> ls[4];
+#pragma unroll
+      for (int be = 0; be < 4; be++) ls[be] = make_c<F>(lc[be].re * is, lc[be].im * is);
+      if (ND > 0) {
+        Cplx<F> Rc[4];
+#pragma unroll
+        for (int al = 0; al < 4; al++) {
+          Rc[al] = cmul(W[cc][0], vp[al * 3 + 0]);
+          cmac(Rc[al], W[cc][1], vp[al * 3 + 1]);
+          cmac(Rc[al], W[cc][2], vp[al * 3 + 2]);
+        }
+#pragma unroll
+        for (int be = 0; be < 4; be++)
+#pragma unroll
+          for (int al = 0; al < 4; al++) cmac_conj(M[be][al], ls[be], Rc[al]);
+      }
+      if (UL == UL_ALL) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          Md[k] = fma(ls[k].re, lc[k].re, Md[k]);
+          Md[k] = fma(ls[k].im, lc[k].im, Md[k]);
+        }
+#pragma unroll
+        for (int k = 4; k < 10; k++) cmac_conj(Mo[k - 4], ls[ul_pair_be(k)], lc[ul_pair_al(k)]);
+      }
+      if (UL == UL_ROT) {
+        Md[0] = fma(ls[0].re, lc[0].re, Md[0]);
+        Md[0] = fma(ls[0].im, lc[0].im, Md[0]);
+        cmac_conj(Mo[0], ls[0], lc[1]);
+        cmac_conj(Mo[1], ls[0], lc[2]);  // needed from roles 0 and 1 only; computing it everywhere keeps the code uniform
+      }
+    }
+    // next stage: the eight running addresses move on (one add each instead of recomputing base + offset)
+    c_full += 8;
+    c_empty += 8;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      a_own[b] += c.stage_bytes;
+      a_nbr[b] += c.stage_bytes;
+    }
+    if (--c_left == 0) {
+      c_left = c.S;
+      c_full = full_u32;
+      c_empty = empty_u32;
+      c_par ^= 1u;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        a_own[b] -= ring_bytes;
+        a_nbr[b] -= ring_bytes;
+      }
     }
   }
 }
@@ -583,10 +650,6 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   args.ul_off = ul_off;
   args.dataPos = static_cast<F *>(dataPos_d);
   args.accumulate = accumulate;
-  {
-    const char *e = getenv("MUGIQ_B200_FUSED_DBG");
-    args.dbg = e ? atoi(e) : 0;
-  }
   if (!choose_tiling(args.tl, grp, g, precision, smem_limit_bytes()))
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);

@@ -64,6 +64,27 @@ __global__ void __launch_bounds__(256) mixed_kernel(double *out, int iters, doub
   if (s == 12345.678) out[0] = s;
 }
 
+// per DFMA, NI independent integer instructions (IMAD chain on separate registers): does non-FP64 issue steal FP64 slots?
+template <int NI, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) dfma_int_kernel(double *out, int iters, double a, double b, int ia) {
+  double x[8];
+  int y[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x[i] = threadIdx.x + i; y[i] = threadIdx.x * i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      x[i] = fma(x[i], a, b);
+#pragma unroll
+      for (int f = 0; f < NI; f++) y[(i + f) & 7] = y[(i + f) & 7] * ia + it;
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += x[i] + y[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) read_kernel(const double2 *__restrict__ in, size_t n, double *out) {
   double s = 0;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,6 +143,18 @@ int main() {
   t = time_ms([&] { mixed_kernel<8><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
   printf(", \"mixed8_tflops\": %.2f, \"mixed8_ms\": %.3f", (nwarps * iters * 8.0 * 256 * 2 + nthreads * iters * 64.0 * 2) / t / 1e9, t);
 
+  // 8 warps per SM (2 per sub-partition), as in the fused loop kernel
+  {
+    const double n8 = (double)sms * 256;
+    t = time_ms([&] { dfma_int_kernel<0, 8><<<sms, 256>>>(out, iters, 1.0000001, 1e-9, 3); }, 5);
+    printf(", \"dfma_8warps_tflops\": %.2f", n8 * iters * 8.0 * 2 / t / 1e9);
+    t = time_ms([&] { dfma_int_kernel<1, 8><<<sms, 256>>>(out, iters, 1.0000001, 1e-9, 3); }, 5);
+    printf(", \"dfma_8warps_1int_tflops\": %.2f", n8 * iters * 8.0 * 2 / t / 1e9);
+    t = time_ms([&] { dfma_int_kernel<2, 8><<<sms, 256>>>(out, iters, 1.0000001, 1e-9, 3); }, 5);
+    printf(", \"dfma_8warps_2int_tflops\": %.2f", n8 * iters * 8.0 * 2 / t / 1e9);
+    t = time_ms([&] { dfma_int_kernel<1, 16><<<sms, 512>>>(out, iters, 1.0000001, 1e-9, 3); }, 5);
+    printf(", \"dfma_16warps_1int_tflops\": %.2f", n8 * 2 * iters * 8.0 * 2 / t / 1e9);
+  }
   const size_t big = (size_t)4 << 30, small = (size_t)64 << 20;
   double2 *buf, *buf2; CK(cudaMalloc(&buf, big)); CK(cudaMalloc(&buf2, big));
   CK(cudaMemset(buf, 0, big)); CK(cudaMemset(buf2, 0, big));
