@@ -198,6 +198,20 @@ long long mugiq_b200_momproj_workspace_bytes(long long M, int N, long long K, in
 int mugiq_b200_momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, int N,
                        long long K, int precision, void *workspace_d, void *stream);
 
+/* ---- stages 3+4 fused: momentum projection straight from dataPos ------------------------------------------------ */
+/* dataMom[t + Lt*((15-G) + 16*iL) + Lt*nData*im] = sum_v3 sign[G] * dataPos[x_eo(v3,t) + V4*(G + 16*iL)] * phase(v3, im).
+ * One call replaces convertIdxOrder_mapGamma (lib/contract_wrappers.cu:133-156) AND cublasZgemm/Cgemm
+ * (lib/loop_mugiq.cpp:364-377): the GEMM reads the position-space buffer in place (for fixed G, iL, t, parity the
+ * V3/2 sites are contiguous), so the reorder pass, its 2 x 16*V4*nLoop complex of HBM traffic and the dataPosMP buffer
+ * disappear.  phase_eo_d holds the phase matrix in the matching even/odd order, phase_eo[s][im][i] with
+ * s = (t + parity) & 1, 2*Nmom*V3/2 complex, built by mugiq_b200_phase_matrix_eo (same arguments as
+ * mugiq_b200_phase_matrix; replaces createPhaseMatrixGPU, lib/contract_wrappers.cu:50-77, for this path). */
+int mugiq_b200_phase_matrix_eo(void *phase_eo_d, const int *mom_h, int Nmom, int ftsign, const int localL[4],
+                               const int totalL[4], const int commCoord[4], int precision, void *stream);
+long long mugiq_b200_momproj_pos_workspace_bytes(const mugiq_b200_geom_t *geom, int nLoop, int Nmom);
+int mugiq_b200_momproj_pos(void *mom_d, const void *dataPos_d, const void *phase_eo_d, int nLoop, int Nmom,
+                           const mugiq_b200_geom_t *geom, void *workspace_d, void *stream);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* Per-kernel launch counters (always on) and CUDA-event timers (while enabled) around every kernel launch
  * of the library, recorded on the stream the kernel is launched on.  The reference only brackets

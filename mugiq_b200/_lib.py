@@ -62,6 +62,9 @@ SYMBOLS = {
     "mugiq_b200_phase_matrix": (_i, [_vp, _pi, _i, _i, _pi, _pi, _pi, _i, _vp]),
     "mugiq_b200_momproj_workspace_bytes": (_ll, [_ll, _i, _ll, _i]),
     "mugiq_b200_momproj": (_i, [_vp, _vp, _vp, _ll, _i, _ll, _i, _vp, _vp]),
+    "mugiq_b200_phase_matrix_eo": (_i, [_vp, _pi, _i, _i, _pi, _pi, _pi, _i, _vp]),
+    "mugiq_b200_momproj_pos_workspace_bytes": (_ll, [_pg, _i, _i]),
+    "mugiq_b200_momproj_pos": (_i, [_vp, _vp, _vp, _i, _i, _pg, _vp, _vp]),
     "mugiq_b200_prof_enable": (_i, [_i]),
     "mugiq_b200_prof_reset": (_i, []),
     "mugiq_b200_prof_num_kernels": (_i, []),

@@ -275,6 +275,46 @@ int mugiq_b200_phase_matrix(void *phase_d, const int *mom_h, int Nmom, int ftsig
   return phase_matrix(phase_d, mom_h, Nmom, ftsign, localL, totalL, commCoord, precision, (cudaStream_t)stream);
 }
 
+int mugiq_b200_phase_matrix_eo(void *phase_eo_d, const int *mom_h, int Nmom, int ftsign, const int localL[4],
+                               const int totalL[4], const int commCoord[4], int precision, void *stream) {
+  const char *who = "mugiq_b200_phase_matrix_eo";
+  REQUIRE_PTR(phase_eo_d, who);
+  REQUIRE_PTR(mom_h, who);
+  REQUIRE_PTR(localL, who);
+  REQUIRE_PTR(totalL, who);
+  if (Nmom < 1) return set_error(MUGIQ_B200_EINVAL, "%s: Nmom = %d must be positive", who, Nmom);
+  if (ftsign != 1 && ftsign != -1) return set_error(MUGIQ_B200_EINVAL, "%s: FTSign must be +1 or -1 (got %d)", who, ftsign);
+  if (precision != MUGIQ_B200_PREC_SINGLE && precision != MUGIQ_B200_PREC_DOUBLE)
+    return set_error(MUGIQ_B200_EINVAL, "%s: precision %d not supported", who, precision);
+  if (localL[0] & 1) return set_error(MUGIQ_B200_EINVAL, "%s: localL[0] = %d must be even", who, localL[0]);
+  for (int i = 0; i < 3; i++)
+    if (localL[i] < 1 || totalL[i] < localL[i])
+      return set_error(MUGIQ_B200_EINVAL, "%s: bad extents in dimension %d (local %d, total %d)", who, i, localL[i], totalL[i]);
+  return phase_matrix_eo(phase_eo_d, mom_h, Nmom, ftsign, localL, totalL, commCoord, precision, (cudaStream_t)stream);
+}
+
+long long mugiq_b200_momproj_pos_workspace_bytes(const mugiq_b200_geom_t *geom, int nLoop, int Nmom) {
+  const char *who = "mugiq_b200_momproj_pos_workspace_bytes";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  if (nLoop < 1 || Nmom < 1) return set_error(MUGIQ_B200_EINVAL, "%s: nLoop = %d, Nmom = %d must be positive", who, nLoop, Nmom);
+  return momproj_pos_workspace_bytes(make_geom(geom->L), nLoop, Nmom, geom->precision);
+}
+
+int mugiq_b200_momproj_pos(void *mom_d, const void *dataPos_d, const void *phase_eo_d, int nLoop, int Nmom,
+                           const mugiq_b200_geom_t *geom, void *workspace_d, void *stream) {
+  const char *who = "mugiq_b200_momproj_pos";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  REQUIRE_PTR(mom_d, who);
+  REQUIRE_PTR(dataPos_d, who);
+  REQUIRE_PTR(phase_eo_d, who);
+  REQUIRE_PTR(workspace_d, who);
+  if (nLoop < 1 || Nmom < 1) return set_error(MUGIQ_B200_EINVAL, "%s: nLoop = %d, Nmom = %d must be positive", who, nLoop, Nmom);
+  return momproj_pos(mom_d, dataPos_d, phase_eo_d, nLoop, Nmom, make_geom(geom->L), geom->precision, workspace_d,
+                     (cudaStream_t)stream);
+}
+
 long long mugiq_b200_momproj_workspace_bytes(long long M, int N, long long K, int precision) {
   if (M < 1 || N < 1 || K < 1)
     return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_momproj_workspace_bytes: bad shape %lld x %d x %lld", M, N, K);

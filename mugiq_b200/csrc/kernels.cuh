@@ -49,6 +49,12 @@ int phase_matrix(void *phase_d, const int *mom_h, int Nmom, int ftsign, const in
 long long momproj_workspace_bytes(long long M, int N, long long K, int precision);
 int momproj(void *mom_d, const void *posMP_d, const void *phase_d, long long M, int N, long long K, int precision,
             void *workspace_d, cudaStream_t stream);
+// stages 3+4 fused (momproj_pos.cu)
+int phase_matrix_eo(void *phase_d, const int *mom_h, int Nmom, int ftsign, const int localL[4], const int totalL[4],
+                    const int commCoord[4], int precision, cudaStream_t stream);
+long long momproj_pos_workspace_bytes(const LatGeom &g, int nLoop, int N, int precision);
+int momproj_pos(void *mom_d, const void *pos_d, const void *phase_eo_d, int nLoop, int N, const LatGeom &g, int precision,
+                void *workspace_d, cudaStream_t stream);
 // layout conversion
 int convert_spinor(void *dst_d, const void *src_d, int order, bool to_site, const LatGeom &g, int precision,
                    cudaStream_t stream);

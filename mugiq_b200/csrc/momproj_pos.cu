@@ -1,0 +1,287 @@
+// momproj_pos.cu — stages 3+4 fused: momentum projection straight from the position-space loop buffer.
+//
+//   dataMom[t + Lt*((15-G) + 16*iL) + Lt*nData*im] = sum_{v3} sign[G] * dataPos[x_eo(v3,t) + V4*(G + 16*iL)] * phase(v3, im)
+//
+// Replaces convertIdxOrder_mapGamma (/root/reference/lib/contract_wrappers.cu:133-156, lib/mugiq_util_kernels.cu:59-99)
+// AND the cuBLAS Zgemm/Cgemm that follows it (lib/loop_mugiq.cpp:364-377): the reorder pass exists only to bring
+// dataPos into the operand order of a column-major GEMM; it moves 2 x 16*V4*nLoop complex through HBM (5.6 GB each
+// way at 24^3x48 with 33 loops) and needs a second buffer of that size.  Here the GEMM reads dataPos in place:
+//  * for fixed (G, iL, t, parity) the V3/2 sites of a time-slice are CONTIGUOUS in dataPos (even/odd order), so that
+//    run is the K dimension of a row of the A operand, read with 128-bit loads, every byte of every sector used;
+//  * the spatial index behind position i of such a run depends on (t + parity) & 1 only (QUDA getCoords: x = 2*(i % Lh)
+//    + ((y + z + t + parity) & 1)), so the phase matrix is stored once in the same even/odd order for both values
+//    of s = (t + parity) & 1:  phase_eo[s][im][i]   (mugiq_b200_phase_matrix_eo);
+//  * the gamma map (G -> 15-G, sign) is applied when the result is written.
+// FP64: DMMA m8n8k4 tiles, complex product embedded in real tiles exactly as in momproj.cu (C^T = P_emb^T A^T); a warp
+// owns the 16 gammas of one (t, iL) - they share t, hence s and the phase operand - for all momenta over a K chunk.
+// FP32: SIMT.  Split-K partial sums are reduced in a fixed order (deterministic).
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace mugiq_b200 {
+
+struct PosGeom {
+  int Lt, V3h, nLoop, N;
+  long long Vh, V4;
+  long long M;  // Lt * 16 * nLoop
+  int kchunk, nchunk;  // chunk of the V3/2 run handled by one task; chunks per run
+};
+
+__device__ __forceinline__ void dmma_m8n8k4_pos(double &c0, double &c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// one warp = one task (t, iL, parity, chunk); NT = number of 4-momentum tiles
+template <int NT>
+__global__ void __launch_bounds__(128)
+momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__ pos, const double *__restrict__ P,
+                        const PosGeom pg, const int n0_base) {
+  constexpr GammaTables gt = gamma_tables();
+  const int lane = threadIdx.x & 31;
+  const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long ntask = (long long)pg.Lt * pg.nLoop * 2 * pg.nchunk;
+  if (task >= ntask) return;
+  const int chunk = (int)(task % pg.nchunk);
+  const int p = (int)((task / pg.nchunk) & 1);
+  const long long pair = task / (2 * pg.nchunk);
+  const int t = (int)(pair % pg.Lt), iL = (int)(pair / pg.Lt);
+  const int s = (t + p) & 1;
+  const int gi = lane >> 2, j = lane & 3, comp = gi & 1;
+  const int kbeg = chunk * pg.kchunk;
+  const int kend = min(pg.V3h, kbeg + pg.kchunk);
+  const int n0 = n0_base;
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  // row of gamma G = mt*8 + gi: sites of (t, parity) start at p*Vh + t*V3h
+  const double2 *arow[2];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+    arow[mt] = reinterpret_cast<const double2 *>(pos) + ((long long)p * pg.Vh + (long long)t * pg.V3h) +
+               pg.V4 * ((mt * 8 + gi) + 16LL * iL);
+  const double2 *prow[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    const int n = n0 + nt * 4 + (gi >> 1);
+    prow[nt] = reinterpret_cast<const double2 *>(P) + ((long long)s * pg.N + (n < pg.N ? n : 0)) * pg.V3h;
+  }
+  for (int k0 = kbeg; k0 < kend; k0 += 4) {
+    const int k = k0 + j;
+    const bool kok = k < kend;
+    double2 d[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) d[mt] = kok ? __ldg(arow[mt] + k) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int n = n0 + nt * 4 + (gi >> 1);
+      const double2 pz = (kok && n < pg.N) ? __ldg(prow[nt] + k) : make_double2(0.0, 0.0);
+      const double a1 = comp ? pz.y : pz.x, a2 = comp ? pz.x : -pz.y;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        dmma_m8n8k4_pos(acc[mt][nt][0], acc[mt][nt][1], a1, d[mt].x);
+        dmma_m8n8k4_pos(acc[mt][nt][0], acc[mt][nt][1], a2, d[mt].y);
+      }
+    }
+  }
+  // c-fragment: row gi -> (n, comp); columns 2j, 2j+1 -> gamma G = mt*8 + 2j + e.  Written under the mapped index.
+  double *out = partial + 2 * (size_t)(p * pg.nchunk + chunk) * (size_t)pg.M * pg.N;
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int n = n0 + nt * 4 + (gi >> 1);
+      if (n < pg.N) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int G = mt * 8 + 2 * j + e;
+          const long long m = t + (long long)pg.Lt * (gt.map_index[G] + 16 * iL);
+          out[2 * (m + pg.M * n) + comp] = (double)gt.map_sign[G] * acc[mt][nt][e];
+        }
+      }
+    }
+}
+
+// SIMT version (FP32): block = (t, iL, parity, chunk), threads stride the K chunk (coalesced); per gamma and momentum a
+// block reduction.  Not a headline path.
+template <typename F>
+__global__ void __launch_bounds__(128)
+momproj_pos_simt_kernel(F *__restrict__ partial, const F *__restrict__ pos, const F *__restrict__ P, const PosGeom pg) {
+  constexpr GammaTables gt = gamma_tables();
+  __shared__ F red[4][2];
+  const long long task = blockIdx.x;
+  const int chunk = (int)(task % pg.nchunk);
+  const int p = (int)((task / pg.nchunk) & 1);
+  const long long pair = task / (2 * pg.nchunk);
+  const int t = (int)(pair % pg.Lt), iL = (int)(pair / pg.Lt);
+  const int s = (t + p) & 1;
+  const int kbeg = chunk * pg.kchunk, kend = min(pg.V3h, kbeg + pg.kchunk);
+  F *out = partial + 2 * (size_t)(p * pg.nchunk + chunk) * (size_t)pg.M * pg.N;
+  for (int G = 0; G < 16; G++) {
+    const F *arow = pos + 2 * (((long long)p * pg.Vh + (long long)t * pg.V3h) + pg.V4 * (G + 16LL * iL));
+    for (int n = 0; n < pg.N; n++) {
+      const F *prow = P + 2 * (((long long)s * pg.N + n) * pg.V3h);
+      Cplx<F> acc = make_c<F>(0, 0);
+      for (int k = kbeg + threadIdx.x; k < kend; k += blockDim.x) cmac(acc, ldg_c<F>(arow + 2 * k), ldg_c<F>(prow + 2 * k));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        acc.re += __shfl_xor_sync(0xffffffffu, acc.re, off);
+        acc.im += __shfl_xor_sync(0xffffffffu, acc.im, off);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5][0] = acc.re;
+        red[threadIdx.x >> 5][1] = acc.im;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        F re = 0, im = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+          re += red[w][0];
+          im += red[w][1];
+        }
+        const long long m = t + (long long)pg.Lt * (gt.map_index[G] + 16 * iL);
+        const F sg = (F)gt.map_sign[G];
+        out[2 * (m + pg.M * n)] = sg * re;
+        out[2 * (m + pg.M * n) + 1] = sg * im;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+splitk_reduce_pos_kernel(F *__restrict__ out, const F *__restrict__ partial, const long long nreal, const int ksplit) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nreal) return;
+  F s = 0;
+  for (int ks = 0; ks < ksplit; ks++) s += partial[(size_t)ks * nreal + i];
+  out[i] = s;
+}
+
+// phase_eo[s][im][i]: the phase of the site behind position i of a (t, parity) run with (t + parity) & 1 == s
+struct PhaseEoArg {
+  int localL[3], totalL[3], commCoord[3];
+  int V3h, Lh, Nmom, ftsign;
+};
+template <typename F>
+__global__ void __launch_bounds__(256) phase_matrix_eo_kernel(F *__restrict__ phase, const int *__restrict__ mom, const PhaseEoArg a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y, s = blockIdx.z;
+  if (i >= a.V3h) return;
+  const int xh = i % a.Lh, yz = i / a.Lh;
+  const int y = yz % a.localL[1], z = yz / a.localL[1];
+  const int x = 2 * xh + ((y + z + s) & 1);
+  const int gx = x + a.commCoord[0] * a.localL[0], gy = y + a.commCoord[1] * a.localL[1], gz = z + a.commCoord[2] * a.localL[2];
+  const double phi = (double)(mom[0 + 3 * im] * gx) / (double)a.totalL[0] + (double)(mom[1 + 3 * im] * gy) / (double)a.totalL[1] +
+                     (double)(mom[2 + 3 * im] * gz) / (double)a.totalL[2];
+  double sn, cs;
+  sincospi(2.0 * phi, &sn, &cs);
+  st_c<F>(phase + 2 * (((size_t)s * a.Nmom + im) * a.V3h + i), make_c<F>((F)cs, (F)((double)a.ftsign * sn)));
+}
+
+int phase_matrix_eo(void *phase_d, const int *mom_h, int Nmom, int ftsign, const int localL[4], const int totalL[4],
+                    const int commCoord[4], int precision, cudaStream_t stream) {
+  PhaseEoArg a;
+  for (int i = 0; i < 3; i++) {
+    a.localL[i] = localL[i];
+    a.totalL[i] = totalL[i];
+    a.commCoord[i] = commCoord ? commCoord[i] : 0;
+  }
+  a.Lh = localL[0] / 2;
+  a.V3h = a.Lh * localL[1] * localL[2];
+  a.Nmom = Nmom;
+  a.ftsign = ftsign;
+  int *mom_d = nullptr;
+  MUGIQ_CUDA_CHECK(cudaMallocAsync((void **)&mom_d, sizeof(int) * 3 * Nmom, stream));
+  MUGIQ_CUDA_CHECK(cudaMemcpyAsync(mom_d, mom_h, sizeof(int) * 3 * Nmom, cudaMemcpyHostToDevice, stream));
+  const dim3 grid((a.V3h + 255) / 256, Nmom, 2);
+  {
+    ProfScope prof(K_PHASE, stream, 2.0 * a.V3h * Nmom * 2.0 * prec_bytes(precision));
+    if (precision == MUGIQ_B200_PREC_DOUBLE)
+      phase_matrix_eo_kernel<double><<<grid, 256, 0, stream>>>((double *)phase_d, mom_d, a);
+    else
+      phase_matrix_eo_kernel<float><<<grid, 256, 0, stream>>>((float *)phase_d, mom_d, a);
+    MUGIQ_LAUNCH_CHECK();
+  }
+  MUGIQ_CUDA_CHECK(cudaFreeAsync(mom_d, stream));
+  MUGIQ_CUDA_CHECK(cudaStreamSynchronize(stream));  // mom_h may be a temporary of the caller
+  return MUGIQ_B200_OK;
+}
+
+static PosGeom make_pos_geom(const LatGeom &g, int nLoop, int N) {
+  PosGeom pg;
+  pg.Lt = g.L[3];
+  pg.V3h = g.V3 / 2;
+  pg.nLoop = nLoop;
+  pg.N = N;
+  pg.Vh = g.volumeCB;
+  pg.V4 = g.volume;
+  pg.M = (long long)g.L[3] * 16 * nLoop;
+  // enough tasks to fill the GPU (148 SMs x 32 warps), at least 64 sites per chunk, at most 16 chunks per run
+  const long long pairs = (long long)pg.Lt * nLoop * 2;
+  long long want = (148LL * 32 + pairs - 1) / pairs;
+  long long maxc = pg.V3h / 64;
+  if (maxc < 1) maxc = 1;
+  if (want > maxc) want = maxc;
+  if (want > 16) want = 16;
+  if (want < 1) want = 1;
+  pg.kchunk = (int)(((pg.V3h + want - 1) / want + 3) / 4 * 4);
+  pg.nchunk = (pg.V3h + pg.kchunk - 1) / pg.kchunk;
+  return pg;
+}
+
+long long momproj_pos_workspace_bytes(const LatGeom &g, int nLoop, int N, int precision) {
+  const PosGeom pg = make_pos_geom(g, nLoop, N);
+  return (long long)2 * pg.nchunk * pg.M * N * 2 * (long long)prec_bytes(precision);
+}
+
+int momproj_pos(void *mom_d, const void *pos_d, const void *phase_eo_d, int nLoop, int N, const LatGeom &g, int precision,
+                void *workspace_d, cudaStream_t stream) {
+  const PosGeom pg = make_pos_geom(g, nLoop, N);
+  const int ksplit = 2 * pg.nchunk;
+  const long long ntask = (long long)pg.Lt * nLoop * ksplit;
+  const double bytes = 2.0 * prec_bytes(precision) * ((double)pg.M * g.V3 + 2.0 * (double)g.V3 * N + (double)pg.M * N * (ksplit + 1));
+  {
+    ProfScope prof(K_MOMPROJ, stream, bytes, 8.0 * (double)pg.M * N * (double)g.V3);
+    if (precision == MUGIQ_B200_PREC_DOUBLE) {
+      const int blocks = (int)((ntask + 3) / 4);
+      const double *A = (const double *)pos_d, *P = (const double *)phase_eo_d;
+      double *ws = (double *)workspace_d;
+      // momenta in passes of up to 36 (9 tiles of 4): A is re-read once per pass
+      for (int n0 = 0; n0 < N; n0 += 36) {
+        const int nt = (std::min(N - n0, 36) + 3) / 4;
+        switch (nt) {
+#define MUGIQ_NT_CASE(k) \
+  case k: momproj_pos_dmma_kernel<k><<<blocks, 128, 0, stream>>>(ws, A, P, pg, n0); break;
+          MUGIQ_NT_CASE(9) MUGIQ_NT_CASE(8) MUGIQ_NT_CASE(7) MUGIQ_NT_CASE(6) MUGIQ_NT_CASE(5)
+          MUGIQ_NT_CASE(4) MUGIQ_NT_CASE(3) MUGIQ_NT_CASE(2)
+          default: momproj_pos_dmma_kernel<1><<<blocks, 128, 0, stream>>>(ws, A, P, pg, n0); break;
+#undef MUGIQ_NT_CASE
+        }
+        MUGIQ_LAUNCH_CHECK();
+      }
+    } else {
+      momproj_pos_simt_kernel<float><<<(unsigned)ntask, 128, 0, stream>>>((float *)workspace_d, (const float *)pos_d,
+                                                                          (const float *)phase_eo_d, pg);
+      MUGIQ_LAUNCH_CHECK();
+    }
+  }
+  const long long nreal = 2 * pg.M * N;
+  const int rblocks = (int)((nreal + 255) / 256);
+  ProfScope prof2(K_SPLITK_REDUCE, stream, (double)nreal * (ksplit + 1) * prec_bytes(precision));
+  if (precision == MUGIQ_B200_PREC_DOUBLE)
+    splitk_reduce_pos_kernel<double><<<rblocks, 256, 0, stream>>>((double *)mom_d, (const double *)workspace_d, nreal, ksplit);
+  else
+    splitk_reduce_pos_kernel<float><<<rblocks, 256, 0, stream>>>((float *)mom_d, (const float *)workspace_d, nreal, ksplit);
+  MUGIQ_LAUNCH_CHECK();
+  return MUGIQ_B200_OK;
+}
+
+}  // namespace mugiq_b200

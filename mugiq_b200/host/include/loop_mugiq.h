@@ -32,6 +32,7 @@ template <typename Float, QudaFieldOrder fieldOrder> class Loop_Mugiq {
   complex<Float> *dataMom_bcast = nullptr;  // host, gathered over "time" ranks
   complex<Float> *phaseMatrix_d = nullptr;
   void *momWorkspace_d = nullptr;
+  bool fusedMomProj = true;                 // stages 3+4 as one kernel on dataPos_d (no dataPosMP_d)
   void *evecStage_d = nullptr;  // site-major staging for QUDA-native eigenvectors
 
   const size_t SizeCplxFloat = sizeof(complex<Float>);

@@ -135,11 +135,16 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
     dataMom = static_cast<complex<Float> *>(calloc(nElemMomLoc, SizeCplxFloat));
     dataMom_bcast = static_cast<complex<Float> *>(calloc(nElemMomTot, SizeCplxFloat));
     if (!dataMom_h || !dataMom || !dataMom_bcast) errorQuda("%s: Could not allocate host momentum-space buffers\n", __func__);
+    // stages 3+4 run as one kernel on dataPos_d (mugiq_b200_momproj_pos): no dataPosMP_d buffer.  MUGIQ_B200_UNFUSED_MOMPROJ=1
+    // selects the reference's two-call form (convertIdxOrder_mapGamma, then the GEMM).
+    fusedMomProj = !(getenv("MUGIQ_B200_UNFUSED_MOMPROJ") && getenv("MUGIQ_B200_UNFUSED_MOMPROJ")[0] == '1');
     HOST_CUDA(cudaMalloc((void **)&phaseMatrix_d, SizeCplxFloat * nElemPhMat));
-    HOST_CUDA(cudaMalloc((void **)&dataPosMP_d, SizeCplxFloat * nElemPosLoc));
+    if (!fusedMomProj) HOST_CUDA(cudaMalloc((void **)&dataPosMP_d, SizeCplxFloat * nElemPosLoc));
     HOST_CUDA(cudaMalloc((void **)&dataMom_d, SizeCplxFloat * nElemMomLoc));
-    const long long ws = mugiq_b200_momproj_workspace_bytes((long long)cPrm->locT * cPrm->nData, cPrm->Nmom, cPrm->locV3,
-                                                            (int)precision_of<Float>());
+    const mugiq_b200_geom_t geom = make_geom(cPrm->localL, precision_of<Float>());
+    const long long ws = fusedMomProj ? mugiq_b200_momproj_pos_workspace_bytes(&geom, cPrm->nLoop, cPrm->Nmom)
+                                      : mugiq_b200_momproj_workspace_bytes((long long)cPrm->locT * cPrm->nData, cPrm->Nmom,
+                                                                           cPrm->locV3, (int)precision_of<Float>());
     if (ws < 0) errorQuda("%s: %s", __func__, mugiq_b200_last_error());
     HOST_CUDA(cudaMalloc(&momWorkspace_d, (size_t)ws));
   }
@@ -177,8 +182,14 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
 }
 
 template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::createPhaseMatrix() {
-  createPhaseMatrixGPU<Float>(phaseMatrix_d, cPrm->momMatrix.data(), cPrm->locV3, cPrm->Nmom, (int)cPrm->FTSign, cPrm->localL,
-                              cPrm->totalL);
+  if (fusedMomProj) {  // same phases, stored in the even/odd run order the fused projection reads
+    const int commCoord[4] = {comm_coord(0), comm_coord(1), comm_coord(2), comm_coord(3)};
+    MUGIQ_CHECK(mugiq_b200_phase_matrix_eo(phaseMatrix_d, cPrm->momMatrix.data(), cPrm->Nmom, (int)cPrm->FTSign, cPrm->localL,
+                                           cPrm->totalL, commCoord, (int)precision_of<Float>(), nullptr));
+  } else {
+    createPhaseMatrixGPU<Float>(phaseMatrix_d, cPrm->momMatrix.data(), cPrm->locV3, cPrm->Nmom, (int)cPrm->FTSign, cPrm->localL,
+                                cPrm->totalL);
+  }
   printfQuda("%s: Phase matrix created\n", __func__);
 }
 
@@ -261,11 +272,16 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   const int locT = cPrm->locT, Nmom = cPrm->Nmom, nLoop = cPrm->nLoop, nData = cPrm->nData;
   if (nData != nLoop * N_GAMMA_) errorQuda("%s: This function assumes that nData = nLoop * NGamma\n", __func__);
 
-  // volume4d-inside-gamma-inside-nLoop -> time-inside-nData-inside-v3, with the Gamma -> g5*Gamma map
-  convertIdxOrder_mapGamma<Float>(dataPosMP_d, dataPos_d, nData, nLoop, cPrm->nParity, cPrm->volumeCB, cPrm->localL);
-  // dataMom(M x N) = dataPosMP(M x K) * phase(K x N), column-major
-  const long long M = (long long)locT * nData, K = locV3;
-  MUGIQ_CHECK(mugiq_b200_momproj(dataMom_d, dataPosMP_d, phaseMatrix_d, M, Nmom, K, (int)precision_of<Float>(), momWorkspace_d, nullptr));
+  if (fusedMomProj) {
+    const mugiq_b200_geom_t geom = make_geom(cPrm->localL, precision_of<Float>());
+    MUGIQ_CHECK(mugiq_b200_momproj_pos(dataMom_d, dataPos_d, phaseMatrix_d, nLoop, Nmom, &geom, momWorkspace_d, nullptr));
+  } else {
+    // volume4d-inside-gamma-inside-nLoop -> time-inside-nData-inside-v3, with the Gamma -> g5*Gamma map
+    convertIdxOrder_mapGamma<Float>(dataPosMP_d, dataPos_d, nData, nLoop, cPrm->nParity, cPrm->volumeCB, cPrm->localL);
+    // dataMom(M x N) = dataPosMP(M x K) * phase(K x N), column-major
+    const long long M = (long long)locT * nData, K = locV3;
+    MUGIQ_CHECK(mugiq_b200_momproj(dataMom_d, dataPosMP_d, phaseMatrix_d, M, Nmom, K, (int)precision_of<Float>(), momWorkspace_d, nullptr));
+  }
   HOST_CUDA(cudaMemcpy(dataMom_h, dataMom_d, SizeCplxFloat * nElemMomLoc, cudaMemcpyDeviceToHost));
   // MPI_Reduce over the "space" ranks and MPI_Gather + MPI_Bcast over the "time" ranks: one rank each
   memcpy(dataMom, dataMom_h, SizeCplxFloat * nElemMomLoc);

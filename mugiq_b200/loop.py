@@ -113,7 +113,7 @@ class Loop_Mugiq:
     """
 
     def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64,
-                 stream_batch=16, copy_pos_to_host=True):
+                 stream_batch=16, copy_pos_to_host=True, fused_momproj=True):
         self.eigsolve = eigsolve_
         self.group = group
         self.evec_batch = int(evec_batch)      # eigenvectors per C-ABI call when they are device resident
@@ -121,6 +121,9 @@ class Loop_Mugiq:
         # the reference always copies dataPos_d to the host (lib/loop_mugiq.cpp:512); a caller that only wants
         # momentum-space data can switch the 16*V4*nLoop-complex D2H copy off
         self.copy_pos_to_host = bool(copy_pos_to_host)
+        # stages 3+4 as one kernel reading dataPos in place (mugiq_b200_momproj_pos) instead of the reference's
+        # convertIdxOrder_mapGamma + GEMM pair; False keeps the two-call form (and its dataPosMP buffer)
+        self.fused_momproj = bool(fused_momproj)
         ev0 = eigsolve_.eVecs[0]
         self.device = torch.device(device) if device is not None else (
             ev0.device if ev0.is_cuda else torch.device("cuda", torch.cuda.current_device()))
@@ -146,6 +149,10 @@ class Loop_Mugiq:
             self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
         self._plan = None
         self._plan_version = -1
+        self._mp_workspace = None
+        if self.cPrm.doMomProj and self.fused_momproj:
+            need = ops.momproj_pos_workspace_bytes(self.L, self.precision, self.cPrm.nLoop, self.cPrm.Nmom)
+            self._mp_workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
 
     # -- lib/loop_mugiq.cpp:102-158 ---------------------------------------------------------------------
     def _allocateDataMemory(self):
@@ -156,14 +163,18 @@ class Loop_Mugiq:
         self.nElemMomTot = p.nG * p.Nmom * p.totT * p.nLoop
         self.nElemPhMat = p.Nmom * p.locV3
         self.dataPos_d = torch.zeros((p.nLoop, p.nG, p.locV4), dtype=self.dtype, device=self.device)
-        if p.doMomProj:
+        if p.doMomProj and not self.fused_momproj:
             self.dataPosMP_d = torch.zeros((p.locV3, p.nData, p.locT), dtype=self.dtype, device=self.device)
 
     def _createPhaseMatrix(self):
         p = self.cPrm
         mom = np.asarray(p.momMatrix, dtype=np.int32).reshape(p.Nmom, 3)
-        self.phaseMatrix_d = ops.phase_matrix(mom, p.FTSign, p.localL, p.totalL, (0, 0, 0, 0), dtype=self.dtype,
-                                              device=self.device)
+        if self.fused_momproj:
+            self.phaseMatrix_d = ops.phase_matrix_eo(mom, p.FTSign, p.localL, p.totalL, (0, 0, 0, 0), dtype=self.dtype,
+                                                     device=self.device)
+        else:
+            self.phaseMatrix_d = ops.phase_matrix(mom, p.FTSign, p.localL, p.totalL, (0, 0, 0, 0), dtype=self.dtype,
+                                                  device=self.device)
 
     # -- lib/loop_mugiq.cpp:440-525 ---------------------------------------------------------------------
     def computeCoarseLoop(self):
@@ -250,9 +261,12 @@ class Loop_Mugiq:
         p = self.cPrm
         if p.nData != p.nLoop * 16:
             raise MugiqError("performMomentumProjection: This function assumes that nData = nLoop * NGamma")
-        ops.reorder_mapgamma(self.dataPosMP_d, self.dataPos_d, p.nData, p.nLoop, self.L)
-        M, N, K = p.locT * p.nData, p.Nmom, p.locV3
-        self.dataMom_d = ops.momproj(self.dataPosMP_d, self.phaseMatrix_d, M, N, K).reshape(p.Nmom, p.nData, p.locT)
+        if self.fused_momproj:
+            self.dataMom_d = ops.momproj_pos(self.dataPos_d, self.phaseMatrix_d, p.nLoop, self.L, workspace=self._mp_workspace)
+        else:
+            ops.reorder_mapgamma(self.dataPosMP_d, self.dataPos_d, p.nData, p.nLoop, self.L)
+            M, N, K = p.locT * p.nData, p.Nmom, p.locV3
+            self.dataMom_d = ops.momproj(self.dataPosMP_d, self.phaseMatrix_d, M, N, K).reshape(p.Nmom, p.nData, p.locT)
         if getattr(self, "_reduce_mom", False):
             import torch.distributed as dist
             dist.all_reduce(torch.view_as_real(self.dataMom_d), op=dist.ReduceOp.SUM, group=self.group)

@@ -230,6 +230,41 @@ def momproj(posMP, phase, M, N, K, workspace=None):
     return out
 
 
+def phase_matrix_eo(mom, ftsign, localL, totalL=None, commCoord=(0, 0, 0, 0), dtype=torch.complex128, device="cuda"):
+    """Phase matrix in the even/odd run order momproj_pos reads: [2 (s = (t+parity)&1), Nmom, V3/2]."""
+    mom = np.ascontiguousarray(np.asarray(mom, dtype=np.int32).reshape(-1, 3))
+    nmom = mom.shape[0]
+    totalL = totalL or localL
+    V3h = int(localL[0]) * int(localL[1]) * int(localL[2]) // 2
+    out = torch.empty((2, nmom, V3h), dtype=dtype, device=device)
+    i4 = C.c_int * 4
+    with torch.cuda.device(out.device):
+        check(_lib.load().mugiq_b200_phase_matrix_eo(out.data_ptr(), mom.ctypes.data_as(_lib._pi), nmom, int(ftsign),
+                                                     i4(*localL), i4(*totalL), i4(*commCoord), _prec(out), _stream()))
+    return out
+
+
+def momproj_pos_workspace_bytes(L, precision, nLoop, nmom):
+    geom = make_geom(L, precision)
+    return check(_lib.load().mugiq_b200_momproj_pos_workspace_bytes(C.byref(geom), int(nLoop), int(nmom)))
+
+
+def momproj_pos(dataPos, phase_eo, nLoop, L, workspace=None):
+    """Momentum projection straight from dataPos [nLoop,16,V4] (stages 3+4 fused).  Returns [Nmom, 16*nLoop, Lt]."""
+    _dev(dataPos, phase_eo, workspace)
+    prec = _prec(dataPos)
+    nmom = phase_eo.shape[1]
+    geom = make_geom(L, prec)
+    need = check(_lib.load().mugiq_b200_momproj_pos_workspace_bytes(C.byref(geom), int(nLoop), int(nmom)))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dataPos.device)
+    out = torch.empty((nmom, 16 * int(nLoop), int(L[3])), dtype=dataPos.dtype, device=dataPos.device)
+    with torch.cuda.device(dataPos.device):
+        check(_lib.load().mugiq_b200_momproj_pos(out.data_ptr(), dataPos.data_ptr(), phase_eo.data_ptr(), int(nLoop), int(nmom),
+                                                 C.byref(geom), workspace.data_ptr(), _stream()))
+    return out
+
+
 # ---- instrumentation (mugiq_b200_prof_*) ---------------------------------------------------------------
 def prof_enable(on=True):
     check(_lib.load().mugiq_b200_prof_enable(int(bool(on))))

@@ -254,6 +254,23 @@ def test_momproj_f64(ops, oracle, M, N, K):
     assert rel_err(host(out), ref) < TOL_F64
 
 
+@pytest.mark.parametrize("L", [(4, 4, 4, 8), (8, 2, 6, 4), (6, 4, 2, 3), (16, 4, 4, 4)])
+@pytest.mark.parametrize("nmom,prec", [(1, 8), (7, 8), (33, 8), (40, 8), (7, 4)])
+def test_momproj_pos_fused(ops, oracle, L, nmom, prec):
+    """Stages 3+4 in one kernel (momentum projection straight from dataPos) against the oracle's reorder + GEMM."""
+    nLoop = 3
+    lat = Lattice(L)
+    rng = np.random.default_rng(5)
+    pos = (rng.standard_normal((nLoop, 16, lat.volume)) + 1j * rng.standard_normal((nLoop, 16, lat.volume))).astype(cdt(prec))
+    mom = rng.integers(-3, 4, size=(nmom, 3)).tolist()
+    mp = oracle.reorder_mapgamma(pos.astype(np.complex128), nLoop, L)
+    ph = oracle.phase_matrix(mom, -1, L)
+    ref = oracle.gemm(mp, ph, L[3] * 16 * nLoop, nmom, lat.V3).reshape(nmom, 16 * nLoop, L[3])
+    ph_eo = ops.phase_matrix_eo(mom, -1, L, dtype=torch.complex128 if prec == 8 else torch.complex64)
+    out = ops.momproj_pos(dev(pos), ph_eo, nLoop, L)
+    assert rel_err(host(out), ref) < (TOL_F64 if prec == 8 else TOL_F32)
+
+
 def test_momproj_f32(ops, oracle):
     M, N, K = 384, 7, 256
     rng = np.random.default_rng(4)
@@ -314,9 +331,9 @@ def test_loop_mugiq_end_to_end(ops, oracle, tmp_path):
     entries = [(0, 1, 1, 1), (1, 0, 1, 2), (3, 1, 2, 2)]
     ref = oracle.compute_loop(ev, sig, U, entries, L)
     ref_mom = npc.momentum_projection(ref, mom, -1, L)
-    for resident in (True, False):
+    for resident, fused in ((True, True), (False, True), (True, False)):
         vecs = [dev(ev[i]) if resident else torch.from_numpy(ev[i]).pin_memory() for i in range(nEv)]
-        loop = computeLoop(prm, Eigsolve(vecs, sig, L), evec_batch=4)
+        loop = computeLoop(prm, Eigsolve(vecs, sig, L), evec_batch=4, fused_momproj=fused)
         assert rel_err(loop.dataPos.numpy(), ref) < TOL_F64
         assert rel_err(loop.dataMom.numpy(), ref_mom) < TOL_F64
         with pytest.raises(MugiqError, match="more than once"):
