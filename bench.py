@@ -211,16 +211,30 @@ def run_ours(args, wl, name):
     L, nev = wl["L"], args.nev or wl["nev"]
     V4 = int(np.prod(L))
     V3 = V4 // L[3]
-    U = synth.random_gauge(L, seed=11)
+    ts = None
+    if args.tsplit:
+        # lattice-T split: every rank owns a slab of wl["L"] of a global lattice with T = L[3] * world; the eigenvectors
+        # span all ranks (same sigma everywhere), the halos of +-t displacements travel over NVLink (NCCL P2P)
+        from mugiq_b200.tsplit import TSplit
+        from mugiq_b200.params import parse_disp_entries
+        tmax = 0
+        if wl["entries"]:
+            _, ds, _, stop = parse_disp_entries(wl["entries"])
+            tmax = max([b for s, b in zip(ds, stop) if s[1] == "t"] + [0])
+        Lg = (L[0], L[1], L[2], L[3] * world)
+        ts = TSplit(Lg, rank, world, tmax)
+        U = synth.random_gauge(Lg, seed=11)
+    else:
+        U = synth.random_gauge(L, seed=11)
     prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
     if wl["entries"]:
         prm.set_displacements(wl["entries"])
     mom = momenta_up_to(wl["p2max"])
     prm.set_momenta(mom)
-    sig = synth.sigmas(nev) + 0.2 * rank
+    sig = synth.sigmas(nev) + (0.0 if ts is not None else 0.2 * rank)
     ev_d = synth.random_evecs_torch(L, nev, seed=100 + rank, device=dev)          # [nev, V4, 12] resident in HBM
     loop = Loop_Mugiq(prm, Eigsolve(list(ev_d), sig, L), device=dev, group=group, evec_batch=args.evec_batch,
-                      copy_pos_to_host=False)
+                      copy_pos_to_host=False, tsplit=ts, stream_batch=50 if ts is not None else 16)
     nLoop = loop.cPrm.nLoop
     units_per_rank = nev * V4 * nLoop
 
@@ -297,7 +311,7 @@ def run_ours(args, wl, name):
 
     # ---- leg 2: end to end through the public API with HOST buffers -----------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and ts is None:
         ev_h = torch.empty((nev, V4, 12), dtype=torch.complex128, pin_memory=True)
         ev_h.copy_(ev_d)
         del loop
@@ -331,9 +345,12 @@ def run_ours(args, wl, name):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": name, "L": list(L), "nev_per_gpu": nev, "entries": wl["entries"], "nLoop": nLoop,
-                           "Nmom": len(mom), "stages": "contract+displace+reorder+momproj" + ("+allreduce" if world > 1 else ""),
+                           "Nmom": len(mom), "stages": "contract+displace+reorder+momproj" + (("+halo exchange+allgather" if ts is not None else "+allreduce") if world > 1 else ""),
                            "l2": f"inputs larger than L2 ({nev * V4 * 192 / 1e9:.2f} GB of eigenvectors read per step)",
-                           "evec_batch": args.evec_batch},
+                           "evec_batch": args.evec_batch,
+                           "partition": ("lattice-T split, global T = %d, halo %d slices, %.1f MB of halo per rank and step over "
+                                         "NVLink" % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector() / 1e6))
+                           if ts is not None else ("eigenvector shards" if world > 1 else "single GPU")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -350,6 +367,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--nev", type=int, default=0, help="override the eigenvector count per GPU (debugging)")
     ap.add_argument("--evec-batch", type=int, default=200)
+    ap.add_argument("--tsplit", action="store_true", help="partition the lattice in T over the GPUs (halo exchange) instead of "
+                                                          "sharding eigenvectors")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -113,7 +113,7 @@ class Loop_Mugiq:
     """
 
     def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64,
-                 stream_batch=16, copy_pos_to_host=True, fused_momproj=True):
+                 stream_batch=16, copy_pos_to_host=True, fused_momproj=True, tsplit=None):
         self.eigsolve = eigsolve_
         self.group = group
         self.evec_batch = int(evec_batch)      # eigenvectors per C-ABI call when they are device resident
@@ -124,6 +124,9 @@ class Loop_Mugiq:
         # stages 3+4 as one kernel reading dataPos in place (mugiq_b200_momproj_pos) instead of the reference's
         # convertIdxOrder_mapGamma + GEMM pair; False keeps the two-call form (and its dataPosMP buffer)
         self.fused_momproj = bool(fused_momproj)
+        # lattice-T split (mugiq_b200.tsplit.TSplit): the eigenvectors given are this rank's time-slab in local even/odd
+        # order, `loopParams_.gauge` is the GLOBAL (replicated) host gauge field, `group` is the group of time ranks
+        self.tsplit = tsplit
         ev0 = eigsolve_.eVecs[0]
         self.device = torch.device(device) if device is not None else (
             ev0.device if ev0.is_cuda else torch.device("cuda", torch.cuda.current_device()))
@@ -133,7 +136,19 @@ class Loop_Mugiq:
         self.precision = PREC_DOUBLE if self.dtype == torch.complex128 else PREC_SINGLE
         self.L = eigsolve_.L
         self.lat = Lattice(self.L)
-        self.cPrm = LoopComputeParam(loopParams_, self.L)
+        if tsplit is not None:
+            if tuple(tsplit.L_loc) != tuple(self.L):
+                raise MugiqError(f"Loop_Mugiq: eigenvectors live on {self.L}, the T split expects {tsplit.L_loc}")
+            if tsplit.world > 1 and group is None:
+                raise MugiqError("Loop_Mugiq: a T split over several ranks needs the process group of the time ranks")
+            self.cPrm = LoopComputeParam(loopParams_, self.L, comm_dim=(1, 1, 1, tsplit.world))
+            tmax = max([b for (d, _, _, b) in self.cPrm.entries() if d == 3] + [0]) if self.cPrm.doNonLocal else 0
+            if tmax > tsplit.H:
+                raise MugiqError(f"Loop_Mugiq: t-displacements up to {tmax} need a halo of {tmax}, the T split has {tsplit.H}")
+            self.L_run = tuple(tsplit.L_ext)  # the kernels run on the slab extended by the halos
+        else:
+            self.cPrm = LoopComputeParam(loopParams_, self.L)
+            self.L_run = self.L
         self.writeDataPos = bool(loopParams_.writePosSpaceHDF5)
         self.writeDataMom = bool(loopParams_.writeMomSpaceHDF5)
         self.momSpaceFilename = loopParams_.fname_mom_h5
@@ -146,7 +161,13 @@ class Loop_Mugiq:
         if self.cPrm.doMomProj:
             self._createPhaseMatrix()
         if self.cPrm.doNonLocal:
-            self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
+            if tsplit is not None:  # replicated global links -> this rank's extended slab
+                import copy
+                lp = copy.copy(loopParams_)
+                lp.gauge = [tsplit.global_slab(np.asarray(loopParams_.gauge[mu]), site_dim=0) for mu in range(4)]
+                self.displace = Displace(lp, self.L_run, dtype=self.dtype, device=self.device)
+            else:
+                self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
         self._plan = None
         self._plan_version = -1
         self._mp_workspace = None
@@ -163,6 +184,9 @@ class Loop_Mugiq:
         self.nElemMomTot = p.nG * p.Nmom * p.totT * p.nLoop
         self.nElemPhMat = p.Nmom * p.locV3
         self.dataPos_d = torch.zeros((p.nLoop, p.nG, p.locV4), dtype=self.dtype, device=self.device)
+        self.dataPosExt_d = None
+        if self.tsplit is not None:
+            self.dataPosExt_d = torch.zeros((p.nLoop, p.nG, Lattice(self.L_run).volume), dtype=self.dtype, device=self.device)
         if p.doMomProj and not self.fused_momproj:
             self.dataPosMP_d = torch.zeros((p.locV3, p.nData, p.locT), dtype=self.dtype, device=self.device)
 
@@ -182,6 +206,9 @@ class Loop_Mugiq:
         es = self.eigsolve
         with torch.cuda.device(self.device):
             plan = self._loop_plan()
+            if self.tsplit is not None:
+                self._accumulate_tsplit(plan)
+                return self._finish_tsplit()
             if es.eVecs[0].is_cuda:
                 for b0 in range(0, es.nEv, self.evec_batch):
                     b1 = min(es.nEv, b0 + self.evec_batch)
@@ -208,6 +235,33 @@ class Loop_Mugiq:
                 self.performMomentumProjection()
         return self
 
+    def _accumulate_tsplit(self, plan):
+        """T split: every eigenvector batch is extended by the neighbours' halo slices (NCCL P2P over NVLink), then
+        the fused kernel runs on the extended slab."""
+        es, ts = self.eigsolve, self.tsplit
+        nb = max(1, min(self.stream_batch, es.nEv))
+        vol = self.lat.volume
+        for b0 in range(0, es.nEv, nb):
+            b1 = min(es.nEv, b0 + nb)
+            inner = torch.stack([es.eVecs[n].reshape(vol, 12).to(self.device, non_blocking=True) for n in range(b0, b1)])
+            ext = ts.extend(inner, group=self.group)
+            plan.accumulate(self.dataPosExt_d, list(ext), es.eVals_sigma[b0:b1], accumulate=b0 > 0)
+        plan.finalize(self.dataPosExt_d)
+
+    def _finish_tsplit(self):
+        p, ts = self.cPrm, self.tsplit
+        # every rank owns its time-slices: no reduction, only the interior of the extended buffer is kept
+        self.dataPos_d.copy_(ts.interior(self.dataPosExt_d, site_dim=2))
+        self._reduce_mom = False
+        if self.copy_pos_to_host:
+            if self.dataPos is None:
+                self.dataPos = torch.empty(self.dataPos_d.shape, dtype=self.dtype, pin_memory=True)
+            self.dataPos.copy_(self.dataPos_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        if p.doMomProj:
+            self.performMomentumProjection()
+        return self
+
     def _loop_plan(self):
         """The Wilson lines + launch schedule for (gauge field, entries): built once, rebuilt when the gauge field
         is uploaded again (Displace.upload_gauge bumps gaugeVersion)."""
@@ -218,7 +272,7 @@ class Loop_Mugiq:
                 self._plan.close()
             entries = p.entries() if p.doNonLocal else []
             gauge = self.displace.gaugeField if self.displace is not None else None
-            self._plan = ops.LoopPlan(gauge, entries, self.L, self.precision)
+            self._plan = ops.LoopPlan(gauge, entries, self.L_run, self.precision)
             self._plan_version = version
         return self._plan
 
@@ -271,9 +325,12 @@ class Loop_Mugiq:
             import torch.distributed as dist
             dist.all_reduce(torch.view_as_real(self.dataMom_d), op=dist.ReduceOp.SUM, group=self.group)
         self.dataMom_h = self.dataMom_d.cpu()
-        # single spatial block and single time block: MPI_Reduce / MPI_Gather / MPI_Bcast are identities
+        # single spatial block: MPI_Reduce over COMM_SPACE is the identity
         self.dataMom = self.dataMom_h
-        self.dataMom_bcast = self.dataMom_h
+        if self.tsplit is not None:  # MPI_Gather over COMM_TIME + MPI_Bcast (lib/loop_mugiq.cpp:420-424)
+            self.dataMom_bcast = self.tsplit.gather_time(self.dataMom_d, group=self.group).cpu()
+        else:
+            self.dataMom_bcast = self.dataMom_h
         self.MomProjDone = True
 
     # -- result access in the reference's HDF5 naming (lib/loop_mugiq.cpp:582-633) -------------------------

@@ -1,0 +1,105 @@
+"""Lattice-T split with halo exchange (SURVEY §8e "secondary partitioning", BASELINE.json config 5): rank r owns the
+global time-slices [r*Tl, (r+1)*Tl).  Spatial displacements need no communication; a displacement of length k in
++-t needs k time-slices of every eigenvector from the neighbouring rank.
+
+Replaces, for a partitioned t-direction, QUDA's per-hop `exchangeGhost` (/root/reference/lib/contract_wrappers.cu:166-174,
+one nFace=1 spinor halo per hop and eigenvector) and the extended gauge field with `exchangeExtendedGhost`
+(lib/displace.cpp:104-134): here each eigenvector batch is extended ONCE by H slices on both sides (H = longest
+t-displacement, rounded up to even so that the even/odd parity of a site is the same in local, extended and global
+coordinates), the fused kernel then runs on the extended lattice (Lt_ext = Tl + 2H) as if it were periodic, and only
+the interior is kept: for interior sites no shift of length <= H wraps, and the plus-direction loops of the lower halo
+are valid too, which is what the minus-from-plus derivation of the interior needs.  In the even/odd site-major layout
+a time-slice is one contiguous chunk per parity, so every halo is two contiguous blocks: they travel as NCCL P2P
+(NVLink) send/recv pairs, batched per eigenvector batch.  The gauge field is replicated (<= 6.1 GB at 48^3x96), each
+rank slices its extended slab once.  The result needs no reduction: each rank owns its time-slices, the projected
+buffers are all-gathered (the reference's COMM_TIME gather, lib/loop_mugiq.cpp:420-424).
+"""
+import numpy as np
+import torch
+
+
+class TSplit:
+    def __init__(self, L_global, rank, world, max_t_disp):
+        Lx, Ly, Lz, T = (int(x) for x in L_global)
+        if T % world:
+            raise ValueError(f"T = {T} is not divisible by {world} ranks")
+        self.rank, self.world = int(rank), int(world)
+        self.Tl = T // world
+        if self.Tl % 2:
+            raise ValueError(f"local T = {self.Tl} must be even (even/odd site order)")
+        H = int(max_t_disp)
+        H += H & 1
+        if H > self.Tl:
+            raise ValueError(f"t-displacements of length {max_t_disp} exceed the local time extent {self.Tl}")
+        self.H = H
+        self.L_global = (Lx, Ly, Lz, T)
+        self.L_loc = (Lx, Ly, Lz, self.Tl)
+        self.L_ext = (Lx, Ly, Lz, self.Tl + 2 * H)
+        self.V3h = Lx * Ly * Lz // 2
+        self.t0 = self.rank * self.Tl  # first global time-slice owned
+
+    # ---- views: a full-lattice even/odd array [..., V4, C...] as [..., parity, t, V3/2, C...] ---------------------------
+    def _view(self, a, Lt, site_dim):
+        shp = list(a.shape)
+        return a.reshape(shp[:site_dim] + [2, Lt, self.V3h] + shp[site_dim + 1:])
+
+    def global_slab(self, field_global, site_dim=0):
+        """Extended slab of this rank cut out of a GLOBAL even/odd field (numpy or torch), periodic in t.  Used for the
+        replicated gauge field and by single-process tests."""
+        v = self._view(field_global, self.L_global[3], site_dim)
+        T = self.L_global[3]
+        ts = [(self.t0 - self.H + i) % T for i in range(self.Tl + 2 * self.H)]
+        idx = torch.as_tensor(ts, device=v.device) if isinstance(v, torch.Tensor) else np.asarray(ts)
+        ext = v.index_select(site_dim + 1, idx) if isinstance(v, torch.Tensor) else np.take(v, idx, axis=site_dim + 1)
+        shp = list(field_global.shape)
+        shp[site_dim] = 2 * (self.Tl + 2 * self.H) * self.V3h
+        return ext.reshape(shp)
+
+    def interior(self, field_ext, site_dim=0):
+        """Interior (owned time-slices) of an extended even/odd array, as a contiguous local-lattice array."""
+        v = self._view(field_ext, self.Tl + 2 * self.H, site_dim)
+        sl = [slice(None)] * v.dim()
+        sl[site_dim + 1] = slice(self.H, self.H + self.Tl)
+        out = v[tuple(sl)]
+        shp = list(field_ext.shape)
+        shp[site_dim] = 2 * self.Tl * self.V3h
+        return out.reshape(shp)
+
+    def extend(self, interior, group=None):
+        """[nb, V4_loc, 12] eigenvectors (local even/odd order) -> [nb, V4_ext, 12] with the halos of both neighbours.
+        world == 1: the halos are the rank's own far slices (plain periodic lattice)."""
+        import torch.distributed as dist
+        nb = interior.shape[0]
+        H, Tl = self.H, self.Tl
+        src = interior.reshape(nb, 2, Tl, self.V3h, -1)
+        ext = torch.empty((nb, 2, Tl + 2 * H, self.V3h, src.shape[-1]), dtype=interior.dtype, device=interior.device)
+        ext[:, :, H:H + Tl] = src
+        if H > 0:
+            top = src[:, :, Tl - H:].contiguous()  # becomes the LOWER halo of the rank above
+            bot = src[:, :, :H].contiguous()       # becomes the UPPER halo of the rank below
+            if self.world == 1:
+                ext[:, :, :H] = top
+                ext[:, :, H + Tl:] = bot
+            else:
+                up, dn = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+                from_dn, from_up = torch.empty_like(top), torch.empty_like(bot)
+                ops = [dist.P2POp(dist.isend, top, up, group), dist.P2POp(dist.isend, bot, dn, group),
+                       dist.P2POp(dist.irecv, from_dn, dn, group), dist.P2POp(dist.irecv, from_up, up, group)]
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                ext[:, :, :H] = from_dn
+                ext[:, :, H + Tl:] = from_up
+        return ext.reshape(nb, 2 * (Tl + 2 * H) * self.V3h, -1)
+
+    def halo_bytes_per_vector(self, itemsize=16):
+        """bytes one eigenvector sends (= receives) per extension: 2 neighbours x H slices x V3 sites x 12 complex"""
+        return 2 * self.H * 2 * self.V3h * 12 * itemsize
+
+    def gather_time(self, local_mom, group=None):
+        """[Nmom, nData, Tl] per rank -> [Nmom, nData, T] on every rank (COMM_TIME gather + broadcast of the reference)."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return local_mom
+        parts = [torch.empty_like(local_mom) for _ in range(self.world)]
+        dist.all_gather(parts, local_mom.contiguous(), group=group)
+        return torch.cat(parts, dim=-1)
