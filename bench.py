@@ -84,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.nv is not None:
