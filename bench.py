@@ -232,9 +232,15 @@ def run_ours(args, wl, name):
     mom = momenta_up_to(wl["p2max"])
     prm.set_momenta(mom)
     sig = synth.sigmas(nev) + (0.0 if ts is not None else 0.2 * rank)
-    ev_d = synth.random_evecs_torch(L, nev, seed=100 + rank, device=dev)          # [nev, V4, 12] resident in HBM
-    loop = Loop_Mugiq(prm, Eigsolve(list(ev_d), sig, L), device=dev, group=group, evec_batch=args.evec_batch,
-                      copy_pos_to_host=False, tsplit=ts, stream_batch=50 if ts is not None else 16)
+    if ts is not None:
+        # the slab is stored in the extended layout (halo slices allocated, filled by the exchange every step)
+        ev_d = synth.random_evecs_torch(ts.L_ext, nev, seed=100 + rank, device=dev)
+        es = Eigsolve(list(ev_d), sig, L, ext_volume=int(np.prod(ts.L_ext)))
+    else:
+        ev_d = synth.random_evecs_torch(L, nev, seed=100 + rank, device=dev)      # [nev, V4, 12] resident in HBM
+        es = Eigsolve(list(ev_d), sig, L)
+    loop = Loop_Mugiq(prm, es, device=dev, group=group, evec_batch=args.evec_batch,
+                      copy_pos_to_host=False, tsplit=ts, stream_batch=100 if ts is not None else 16)
     nLoop = loop.cPrm.nLoop
     units_per_rank = nev * V4 * nLoop
 

@@ -29,7 +29,9 @@ class Eigsolve:
     or HOST tensors when the loop streams them) and `eVals_sigma[n]` (host floats, sigma_n = sqrt(lambda_n),
     lib/eigsolve_mugiq.cpp:289-315).  `L` are the local lattice extents the fields live on."""
 
-    def __init__(self, eVecs, eVals_sigma, L):
+    def __init__(self, eVecs, eVals_sigma, L, ext_volume=0):
+        # ext_volume: sites of the T-split extended slab when the fields are stored with their halo slices allocated
+        self.ext_volume = int(ext_volume)
         self.eVecs = list(eVecs)
         self.eVals_sigma = [float(s) for s in eVals_sigma]
         self.L = tuple(int(x) for x in L)
@@ -40,7 +42,7 @@ class Eigsolve:
             raise MugiqError("Eigsolve: eVals_sigma length does not match the number of eigenvectors")
         vol = Lattice(self.L).volume
         for v in self.eVecs:
-            if v.numel() != vol * 12 or not v.is_complex():
+            if (v.numel() != vol * 12 and v.numel() != self.ext_volume * 12) or not v.is_complex():
                 raise MugiqError("Eigsolve: eigenvectors must be complex fields of volume*12 elements "
                                  "(full site subset, lib/contract_wrappers.cu:100)")
 
@@ -240,11 +242,15 @@ class Loop_Mugiq:
         the fused kernel runs on the extended slab."""
         es, ts = self.eigsolve, self.tsplit
         nb = max(1, min(self.stream_batch, es.nEv))
-        vol = self.lat.volume
-        for b0 in range(0, es.nEv, nb):
-            b1 = min(es.nEv, b0 + nb)
-            inner = torch.stack([es.eVecs[n].reshape(vol, 12).to(self.device, non_blocking=True) for n in range(b0, b1)])
-            ext = ts.extend(inner, group=self.group)
+        batches = [(b0, min(es.nEv, b0 + nb)) for b0 in range(0, es.nEv, nb)]
+        # the halo exchange of batch i+1 is posted before the kernels of batch i are launched, so it overlaps them
+        pending = ts.begin_extend(es.eVecs[batches[0][0]:batches[0][1]], group=self.group, device=self.device)
+        for i, (b0, b1) in enumerate(batches):
+            cur = pending
+            if i + 1 < len(batches):
+                n0, n1 = batches[i + 1]
+                pending = ts.begin_extend(es.eVecs[n0:n1], group=self.group, device=self.device)
+            ext = ts.finish_extend(cur)
             plan.accumulate(self.dataPosExt_d, list(ext), es.eVals_sigma[b0:b1], accumulate=b0 > 0)
         plan.finalize(self.dataPosExt_d)
 

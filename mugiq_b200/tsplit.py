@@ -18,6 +18,18 @@ import numpy as np
 import torch
 
 
+def _as_batch(views):
+    """[nb, ...] strided view over equally spaced, equally shaped contiguous tensors of one storage, else None."""
+    v0 = views[0]
+    if len(views) == 1:
+        return v0.unsqueeze(0)
+    step = (views[1].data_ptr() - v0.data_ptr()) // v0.element_size()
+    if step <= 0 or not all(v.is_contiguous() and v.untyped_storage().data_ptr() == v0.untyped_storage().data_ptr() and
+                            v.data_ptr() == v0.data_ptr() + k * step * v0.element_size() for k, v in enumerate(views)):
+        return None
+    return torch.as_strided(v0, (len(views),) + tuple(v0.shape), (step,) + tuple(v0.stride()), v0.storage_offset())
+
+
 class TSplit:
     def __init__(self, L_global, rank, world, max_t_disp):
         Lx, Ly, Lz, T = (int(x) for x in L_global)
@@ -65,31 +77,72 @@ class TSplit:
         shp[site_dim] = 2 * self.Tl * self.V3h
         return out.reshape(shp)
 
+    def begin_extend(self, vectors, group=None, device=None):
+        """Starts the extension of a batch of eigenvectors (sequence of [V4_loc, 12] tensors in local even/odd order, or
+        one [nb, V4_loc, 12] tensor): the interiors are written into the extended buffer and the halo send/recv pairs are
+        posted (asynchronously: they overlap whatever is launched before finish_extend).  Returns a handle."""
+        import torch.distributed as dist
+        nb = len(vectors)
+        H, Tl = self.H, self.Tl
+        v0 = vectors[0]
+        device = device if device is not None else v0.device
+        ncomp = 12
+        if v0.numel() == 2 * (Tl + 2 * H) * self.V3h * ncomp and v0.device == torch.device(device) and H > 0:
+            # the caller already stores its slab in the extended layout (halo slices allocated, interior filled): only the
+            # halos move, nothing is copied
+            views = [v.reshape(2, Tl + 2 * H, self.V3h, ncomp) for v in vectors]
+            batch = _as_batch(views)  # one strided view when the fields are slices of one allocation: 2 copies, not 2*nb
+            h = {"ext": None, "views": views, "batch": batch, "reqs": [], "from_dn": None, "from_up": None}
+            if batch is not None:
+                top, bot = batch[:, :, Tl:Tl + H].contiguous(), batch[:, :, H:2 * H].contiguous()
+            else:
+                top = torch.stack([v[:, Tl:Tl + H] for v in views])
+                bot = torch.stack([v[:, H:2 * H] for v in views])
+        else:
+            ext = torch.empty((nb, 2, Tl + 2 * H, self.V3h, ncomp), dtype=v0.dtype, device=device)
+            for k in range(nb):
+                ext[k, :, H:H + Tl].copy_(vectors[k].reshape(2, Tl, self.V3h, ncomp), non_blocking=True)
+            h = {"ext": ext, "views": None, "reqs": [], "from_dn": None, "from_up": None}
+            if H > 0:
+                top = ext[:, :, Tl:Tl + H].contiguous()  # owned slices Tl-H..Tl-1: the LOWER halo of the rank above
+                bot = ext[:, :, H:2 * H].contiguous()    # owned slices 0..H-1: the UPPER halo of the rank below
+        if H > 0:
+            if self.world == 1:
+                h["from_dn"], h["from_up"] = top, bot
+            else:
+                up, dn = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+                h["from_dn"], h["from_up"] = torch.empty_like(top), torch.empty_like(bot)
+                ops = [dist.P2POp(dist.isend, top, up, group), dist.P2POp(dist.isend, bot, dn, group),
+                       dist.P2POp(dist.irecv, h["from_dn"], dn, group), dist.P2POp(dist.irecv, h["from_up"], up, group)]
+                h["reqs"] = dist.batch_isend_irecv(ops)
+                h["keep"] = (top, bot)  # the send buffers must outlive the transfers
+        return h
+
+    def finish_extend(self, h):
+        """Waits for the halos of a begin_extend handle and returns the extended batch ([nb, V4_ext, 12], or the list of
+        the caller's own extended vectors when they were extended in place)."""
+        H, Tl = self.H, self.Tl
+        for req in h["reqs"]:
+            req.wait()
+        if h["views"] is not None:
+            if h["batch"] is not None:
+                h["batch"][:, :, :H] = h["from_dn"]
+                h["batch"][:, :, H + Tl:] = h["from_up"]
+            else:
+                for k, v in enumerate(h["views"]):
+                    v[:, :H] = h["from_dn"][k]
+                    v[:, H + Tl:] = h["from_up"][k]
+            return [v.reshape(2 * (Tl + 2 * H) * self.V3h, -1) for v in h["views"]]
+        ext = h["ext"]
+        if H > 0:
+            ext[:, :, :H] = h["from_dn"]
+            ext[:, :, H + Tl:] = h["from_up"]
+        return ext.reshape(ext.shape[0], 2 * (Tl + 2 * H) * self.V3h, -1)
+
     def extend(self, interior, group=None):
         """[nb, V4_loc, 12] eigenvectors (local even/odd order) -> [nb, V4_ext, 12] with the halos of both neighbours.
         world == 1: the halos are the rank's own far slices (plain periodic lattice)."""
-        import torch.distributed as dist
-        nb = interior.shape[0]
-        H, Tl = self.H, self.Tl
-        src = interior.reshape(nb, 2, Tl, self.V3h, -1)
-        ext = torch.empty((nb, 2, Tl + 2 * H, self.V3h, src.shape[-1]), dtype=interior.dtype, device=interior.device)
-        ext[:, :, H:H + Tl] = src
-        if H > 0:
-            top = src[:, :, Tl - H:].contiguous()  # becomes the LOWER halo of the rank above
-            bot = src[:, :, :H].contiguous()       # becomes the UPPER halo of the rank below
-            if self.world == 1:
-                ext[:, :, :H] = top
-                ext[:, :, H + Tl:] = bot
-            else:
-                up, dn = (self.rank + 1) % self.world, (self.rank - 1) % self.world
-                from_dn, from_up = torch.empty_like(top), torch.empty_like(bot)
-                ops = [dist.P2POp(dist.isend, top, up, group), dist.P2POp(dist.isend, bot, dn, group),
-                       dist.P2POp(dist.irecv, from_dn, dn, group), dist.P2POp(dist.irecv, from_up, up, group)]
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-                ext[:, :, :H] = from_dn
-                ext[:, :, H + Tl:] = from_up
-        return ext.reshape(nb, 2 * (Tl + 2 * H) * self.V3h, -1)
+        return self.finish_extend(self.begin_extend(interior, group=group))
 
     def halo_bytes_per_vector(self, itemsize=16):
         """bytes one eigenvector sends (= receives) per extension: 2 neighbours x H slices x V3 sites x 12 complex"""

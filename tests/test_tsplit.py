@@ -55,7 +55,15 @@ def test_geometry_and_parity_bookkeeping():
 def test_single_rank_extension_is_the_periodic_wrap():
     g = torch.from_numpy(_global_field())
     ts = TSplit(L, 0, 1, max_t_disp=2)
-    assert torch.equal(ts.extend(g), ts.global_slab(g, site_dim=1))
+    want = ts.global_slab(g, site_dim=1)
+    assert torch.equal(ts.extend(g), want)
+    # in-place form: the caller's fields already have the halo slices allocated, only the halos are (re)written
+    stored = want.clone()
+    v = stored.reshape(-1, 2, ts.Tl + 2 * ts.H, ts.V3h, 12)
+    v[:, :, :ts.H] = 0
+    v[:, :, ts.H + ts.Tl:] = 0
+    out = ts.finish_extend(ts.begin_extend(list(stored)))
+    assert all(o.data_ptr() == s.data_ptr() for o, s in zip(out, stored)) and torch.equal(torch.stack(out), want)
 
 
 def _free_port():
@@ -111,8 +119,8 @@ def test_tsplit_loop_matches_global_oracle(oracle, world, monkeypatch):
     pos_parts, mom_parts = [], []
     for rank in range(world):
         ts = TSplit(Lg, rank, world, max_t_disp=2)
-        monkeypatch.setattr(ts, "extend", lambda inner, group=None, ts=ts: ts.global_slab(evg[:inner.shape[0]], site_dim=1)
-                            if inner.shape[0] == nEv else None)
+        monkeypatch.setattr(ts, "begin_extend", lambda vecs, group=None, device=None, ts=ts: len(vecs))
+        monkeypatch.setattr(ts, "finish_extend", lambda n, ts=ts: ts.global_slab(evg[:n], site_dim=1))
         prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
         prm.set_displacements(entries_str)
         prm.set_momenta(mom)
