@@ -412,3 +412,47 @@ def test_full_size_properties(ops):
     dm = ops.momproj(mp, ph, L[3] * 16 * nLoop, 1, lat.V3).reshape(16 * nLoop, L[3])
     ssum = mp.sum(dim=0)
     assert float((dm - ssum).abs().max() / ssum.abs().max()) < TOL_F64
+
+
+def test_config3_lattice_properties(ops, monkeypatch):
+    """BASELINE.json configs[2] lattice and loop set (24^3x48, displacements of length 1..4 in all 8 directions, momenta
+    |p|^2 <= 4) with a few eigenvectors.  No oracle at this size: the derived minus loops (identity, one pass over the
+    loop buffer) must equal the minus loops computed directly with their own Wilson lines, batches must add up, and
+    the one-kernel projection must equal reorder + GEMM."""
+    from mugiq_b200.params import parse_disp_entries, which_displace
+    L = (24, 24, 24, 48)
+    lat = Lattice(L)
+    nEv = 3
+    U = synth.random_gauge(L, seed=70)
+    gd = ops.gauge_upload(U, L)
+    ev = synth.random_evecs_torch(L, nEv, seed=70)
+    sig = synth.sigmas(nEv)
+    _, ds, a, b = parse_disp_entries(synth.UP_TO_4_ENTRIES)
+    entries = [which_displace(s) + (x, y) for s, x, y in zip(ds, a, b)]
+    plan = ops.LoopPlan(gd, entries, L)
+    info = plan.info()
+    assert plan.nLoop == 33 and info["computed"] == 17 and info["derived"] == 16
+    assert info["wilson_bytes"] == 12 * lat.volume * 144   # plus chains of 2, 3, 4 links in 4 directions
+    sym = torch.zeros((33, 16, lat.volume), dtype=torch.complex128, device="cuda")
+    plan.accumulate(sym, list(ev[:2]), sig[:2], accumulate=False)
+    plan.accumulate(sym, list(ev[2:]), sig[2:], accumulate=True)
+    plan.finalize(sym)
+    plan.close()
+    monkeypatch.setenv("MUGIQ_B200_NO_PM_SYMMETRY", "1")
+    direct_plan = ops.LoopPlan(gd, entries, L)
+    assert direct_plan.info()["computed"] == 33
+    direct = torch.zeros_like(sym)
+    direct_plan.accumulate(direct, list(ev), sig, accumulate=False)
+    direct_plan.finalize(direct)
+    direct_plan.close()
+    scale = float(direct.abs().max())
+    assert float((sym - direct).abs().max()) / scale < TOL_F64
+    assert abs(complex(sym[0, 0].sum()) - (1.0 / sig).sum()) < 1e-10 * (1.0 / sig).sum()
+    del direct
+    mom = momenta_up_to(4)
+    assert len(mom) == 33
+    fused = ops.momproj_pos(sym, ops.phase_matrix_eo(mom, -1, L), 33, L)
+    mp = torch.empty((lat.V3, 16 * 33, L[3]), dtype=torch.complex128, device="cuda")
+    ops.reorder_mapgamma(mp, sym, 16 * 33, 33, L)
+    two = ops.momproj(mp, ops.phase_matrix(mom, -1, L), L[3] * 16 * 33, 33, lat.V3).reshape(33, 16 * 33, L[3])
+    assert float((fused - two).abs().max() / two.abs().max()) < TOL_F64
