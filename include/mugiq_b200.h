@@ -111,6 +111,10 @@ int mugiq_b200_ingest_spinor(void *dst_site_d, const void *src_d, int src_order,
                              const mugiq_b200_geom_t *geom, void *stream);
 int mugiq_b200_export_spinor(void *dst_d, int dst_order, const void *src_site_d,
                              const mugiq_b200_geom_t *geom, void *stream);
+/* nfields conversions in one launch (HOST arrays of device pointers): what a QUDA-backed caller uses per eigenvector
+ * batch, one 50 MB field per launch leaves the GPU mostly idle. */
+int mugiq_b200_ingest_spinor_batch(void *const *dst_site_d, const void *const *src_d, int nfields, int src_order,
+                                   const mugiq_b200_geom_t *geom, void *stream);
 /* Host QDP-order gauge (void* gauge[4], one pointer per direction, MugiqLoopParam::gauge,
  * include/mugiq.h:43) -> device [mu][parity][x_cb][3][3].  Replaces Displace::createCudaGaugeField /
  * createExtendedCudaGaugeField for an unpartitioned lattice (lib/displace.cpp:70-134).  Synchronous. */

@@ -46,6 +46,7 @@ SYMBOLS = {
     "mugiq_b200_gamma_tables": (_i, [_pd, _pi, _pd, _pi]),
     "mugiq_b200_ingest_spinor": (_i, [_vp, _vp, _i, _pg, _vp]),
     "mugiq_b200_export_spinor": (_i, [_vp, _i, _vp, _pg, _vp]),
+    "mugiq_b200_ingest_spinor_batch": (_i, [_pvp, _pvp, _i, _i, _pg, _vp]),
     "mugiq_b200_gauge_upload": (_i, [_vp, _pvp, _pg, _vp]),
     "mugiq_b200_contract": (_i, [_vp, _vp, _vp, _d, _pg, _vp]),
     "mugiq_b200_contract_batch": (_i, [_vp, _pvp, _pvp, _pd, _i, _i, _pg, _vp]),

@@ -128,6 +128,22 @@ int mugiq_b200_ingest_spinor(void *dst_site_d, const void *src_d, int src_order,
   return convert_spinor(dst_site_d, src_d, src_order, true, g, geom->precision, (cudaStream_t)stream);
 }
 
+int mugiq_b200_ingest_spinor_batch(void *const *dst_site_d, const void *const *src_d, int nfields, int src_order,
+                                   const mugiq_b200_geom_t *geom, void *stream) {
+  const char *who = "mugiq_b200_ingest_spinor_batch";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  REQUIRE_PTR(dst_site_d, who);
+  REQUIRE_PTR(src_d, who);
+  if (nfields < 0) return set_error(MUGIQ_B200_EINVAL, "%s: nfields = %d", who, nfields);
+  if (src_order != MUGIQ_B200_ORDER_FLOAT2 && src_order != MUGIQ_B200_ORDER_FLOAT4)
+    return set_error(MUGIQ_B200_EINVAL, "%s: source order must be FLOAT2 or FLOAT4 (got %d)", who, src_order);
+  for (int i = 0; i < nfields; i++)
+    if (!dst_site_d[i] || !src_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: field %d is NULL", who, i);
+  return convert_spinor_batch(dst_site_d, src_d, nfields, src_order, true, make_geom(geom->L), geom->precision,
+                              (cudaStream_t)stream);
+}
+
 int mugiq_b200_export_spinor(void *dst_d, int dst_order, const void *src_site_d, const mugiq_b200_geom_t *geom,
                              void *stream) {
   const char *who = "mugiq_b200_export_spinor";

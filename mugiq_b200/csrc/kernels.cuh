@@ -58,5 +58,7 @@ int momproj_pos(void *mom_d, const void *pos_d, const void *phase_eo_d, int nLoo
 // layout conversion
 int convert_spinor(void *dst_d, const void *src_d, int order, bool to_site, const LatGeom &g, int precision,
                    cudaStream_t stream);
+int convert_spinor_batch(void *const *dst_d, const void *const *src_d, int n, int order, bool to_site, const LatGeom &g,
+                         int precision, cudaStream_t stream);
 
 }  // namespace mugiq_b200

@@ -233,21 +233,21 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   const size_t fieldBytes = eigsolve->eVecs[0]->Bytes();
   const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
   if (native && !evecStage_d) HOST_CUDA(cudaMalloc(&evecStage_d, fieldBytes * batch));
-  std::vector<const void *> ptr(batch);
+  std::vector<const void *> ptr(batch), src(batch);
+  std::vector<void *> stage(batch);
   std::vector<double> sigma(batch);
   for (int n0 = 0; n0 < nEv; n0 += batch) {
     const int nb = std::min(batch, nEv - n0);
     for (int i = 0; i < nb; i++) {
       ColorSpinorField *v = eigsolve->eVecs[n0 + i];
       sigma[i] = (double)(Float)(*(eigsolve->eVals_sigma))[n0 + i];
-      if (native) {
-        void *dst = static_cast<char *>(evecStage_d) + (size_t)i * fieldBytes;
-        MUGIQ_CHECK(mugiq_b200_ingest_spinor(dst, v->V(), abi_order(v->FieldOrder()), &geom, nullptr));
-        ptr[i] = dst;
-      } else {
-        ptr[i] = v->V();
-      }
+      if (v->FieldOrder() != fieldOrder) errorQuda("%s: eigenvector %d has field order %d, expected %d", __func__, n0 + i, (int)v->FieldOrder(), (int)fieldOrder);
+      src[i] = v->V();
+      stage[i] = native ? static_cast<char *>(evecStage_d) + (size_t)i * fieldBytes : nullptr;
+      ptr[i] = native ? stage[i] : v->V();
     }
+    if (native)  // the whole batch in one launch
+      MUGIQ_CHECK(mugiq_b200_ingest_spinor_batch(stage.data(), src.data(), nb, abi_order(fieldOrder), &geom, nullptr));
     MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0, nullptr));
     printfQuda("%s: Loop trace for eigenvectors %04d - %04d completed\n", __func__, n0, n0 + nb - 1);
   }

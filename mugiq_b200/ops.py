@@ -76,6 +76,19 @@ def ingest_spinor(src, order, L):
     return dst
 
 
+def ingest_spinor_batch(srcs, order, L):
+    """QUDA-native fields -> one [n, V4, 12] site-major tensor, one launch."""
+    _dev(*srcs)
+    n = len(srcs)
+    dst = torch.empty((n, _volume(L), 12), dtype=srcs[0].dtype, device=srcs[0].device)
+    geom = make_geom(L, _prec(srcs[0]))
+    with torch.cuda.device(dst.device):
+        check(_lib.load().mugiq_b200_ingest_spinor_batch(ptr_array([dst[i].data_ptr() for i in range(n)]),
+                                                         ptr_array([s.data_ptr() for s in srcs]), n, order, C.byref(geom),
+                                                         _stream()))
+    return dst
+
+
 def export_spinor(src_site, order, L):
     _dev(src_site)
     dst = torch.empty_like(src_site)
