@@ -246,15 +246,12 @@ __device__ __forceinline__ void tma_bulk_g2s_if(uint32_t dst, const void *src_gm
 template <typename F, int ND, int UL>
 __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx<F> &c, const Cplx<F> (&W)[3][3],
                                           Cplx<F> (&M)[4][4], F (&Md)[4], Cplx<F> (&Mo)[6], const bool opposite) {
-  // producer side: this warp issues copies c.warp, c.warp + nActive, ... of every stage.  With the preferred tile
-  // (4 consecutive-y rows) a stage is 6-8 copies, i.e. at most one per warp: its descriptor lives in registers.
-  uint32_t my_tx = 0;
-  for (int i = c.warp; i < c.st->ncopies; i += c.nActive) my_tx += (uint32_t)c.st->cp_bytes[i];
-  const bool has_copy = c.warp < c.st->ncopies;
-  const bool more_copies = c.warp + c.nActive < c.st->ncopies;
-  const uint32_t cp0_s = has_copy ? (uint32_t)c.st->cp_soff[c.warp] : 0u;
-  const uint32_t cp0_b = has_copy ? (uint32_t)c.st->cp_bytes[c.warp] : 0u;
-  const size_t cp0_g = has_copy ? ((size_t)c.st->cp_goff16[c.warp] << 4) : 0;
+  // producer side: the warps take turns - warp (m mod nActive) issues ALL bulk copies of eigenvector m's stage (lane i
+  // issues copy i), the others only advance their cursors.  Issuing costs ~100 non-FP64 instructions, which on this
+  // chip are paid in FP64 issue slots; spread over the warps in turn it is ~15 per warp and eigenvector instead of ~65
+  // when every warp issued its own share every time.
+  uint32_t total_tx = 0;
+  for (int i = 0; i < c.st->ncopies; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
   const int lead = c.lane == 0;
   const uint32_t stages_u32 = smem_u32(c.stages);
   const uint32_t full_u32 = smem_u32(c.full), empty_u32 = smem_u32(c.empty);
@@ -264,15 +261,18 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
   uint32_t p_full = full_u32, p_empty = empty_u32, p_dst = stages_u32;  // producer cursor (stage of the next issue)
   int p_left = c.S;                                                      // stages until the cursor wraps
   uint32_t p_par = 1;  // parity to wait for on the empty barrier; the first pass over the ring does not wait
+  int turn = c.warp;   // issues when it reaches 0
   auto issue_share = [&](int m, bool wait) {
-    if (wait) mbar_wait_u32(p_empty, p_par);
-    const char *ev = static_cast<const char *>(A.vt.evec[m]);
-    mbar_expect_tx_if(p_full, my_tx, lead);
-    tma_bulk_g2s_if(p_dst + cp0_s, ev + cp0_g, cp0_b, p_full, lead && has_copy);
-    if (more_copies)
-      for (int i = c.warp + c.nActive; i < c.st->ncopies; i += c.nActive)
+    if (turn == 0) {  // warp-uniform
+      if (wait) mbar_wait_u32(p_empty, p_par);
+      const char *ev = static_cast<const char *>(A.vt.evec[m]);
+      mbar_expect_tx_if(p_full, total_tx, lead);
+      for (int i = c.lane; i < c.st->ncopies; i += 32)
         tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4), (uint32_t)c.st->cp_bytes[i],
-                        p_full, lead);
+                        p_full, 1);
+      turn = c.nActive;
+    }
+    turn--;
     p_full += 8;
     p_empty += 8;
     p_dst += (uint32_t)c.stage_bytes;
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   if (threadIdx.x == 0) {
     build_slots(st, A.grp, tl, g, kSite, y0, z0, t0);
     for (int s = 0; s < tl.nstages; s++) {
-      mbar_init(&full[s], nActive);  // one arrive.expect_tx per issuing warp
+      mbar_init(&full[s], 1);        // one arrive.expect_tx by the warp whose turn it is
       mbar_init(&empty[s], nActive);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -85,6 +85,29 @@ __global__ void __launch_bounds__(WARPS * 32) dfma_int_kernel(double *out, int i
   if (s == 12345.678) out[0] = s;
 }
 
+// DFMA whose three source operands are all distinct registers (no constant, no operand reuse): acc[i] += y[j] * z[k]
+// NY y-values x NZ z-values -> NY*NZ accumulators, as in the colour trace of the fused kernel (4 x 4)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) dfma3_kernel(double *out, int iters, const double *in) {
+  double y[4], z[4], acc[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { y[i] = in[threadIdx.x + i]; z[i] = in[threadIdx.x + 4 + i]; }
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[j * 4 + k] = fma(y[j], z[k], acc[j * 4 + k]);
+    // keep y, z changing so that the compiler cannot hoist anything (2 extra FP64 ops per 16)
+    y[it & 3] += 1e-9;
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += acc[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) read_kernel(const double2 *__restrict__ in, size_t n, double *out) {
   double s = 0;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,6 +177,14 @@ int main() {
     printf(", \"dfma_8warps_2int_tflops\": %.2f", n8 * iters * 8.0 * 2 / t / 1e9);
     t = time_ms([&] { dfma_int_kernel<1, 16><<<sms, 512>>>(out, iters, 1.0000001, 1e-9, 3); }, 5);
     printf(", \"dfma_16warps_1int_tflops\": %.2f", n8 * 2 * iters * 8.0 * 2 / t / 1e9);
+  }
+  {
+    double *zin; CK(cudaMalloc(&zin, 4096 * 8)); CK(cudaMemset(zin, 0, 4096 * 8));
+    const double n8 = (double)sms * 256;
+    t = time_ms([&] { dfma3_kernel<8><<<sms, 256>>>(out, iters, zin); }, 5);
+    printf(", \"dfma_3distinct_8warps_tflops\": %.2f", n8 * iters * 16.0 * 2 / t / 1e9);
+    t = time_ms([&] { dfma3_kernel<16><<<sms, 512>>>(out, iters, zin); }, 5);
+    printf(", \"dfma_3distinct_16warps_tflops\": %.2f", n8 * 2 * iters * 16.0 * 2 / t / 1e9);
   }
   const size_t big = (size_t)4 << 30, small = (size_t)64 << 20;
   double2 *buf, *buf2; CK(cudaMalloc(&buf, big)); CK(cudaMalloc(&buf2, big));
