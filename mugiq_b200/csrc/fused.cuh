@@ -35,10 +35,8 @@ struct FusedTiling {
   int nTy, nTz, nTt;     // tiles per dimension
   int units;             // warps per loop: ceil(sitesPerTile / 32)
   int nslots;            // staged rows per eigenvector (own + de-duplicated shifted rows), <= kFusedMaxSlots
-  int hr_stride;         // bytes between consecutive half-rows of a stage in shared memory
-  int stage_bytes;       // nslots * 2 * hr_stride
+  int stage_bytes;       // nslots * 2 half-rows of Lx/2 sites, rounded up to 128 B
   int nstages;
-  int skew;              // bytes of destination skew per (slot & 3): 16 = conflict-free reads, 0 = 128-B aligned rows
 };
 
 struct FusedVecTable {

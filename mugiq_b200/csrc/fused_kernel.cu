@@ -45,32 +45,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA, non-tensor form); bytes and both addresses are multiples of 16
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // ---- staged-row ("slot") table of a tile: shared by host (sizing) and device -------------------------------
 constexpr int kMaxCopies = 2 * kFusedMaxSlots;
@@ -582,9 +556,7 @@ static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom 
     SlotTable st;
     build_slots(st, grp, tl, g, site, 0, 0, 0);
     tl.nslots = st.nslots;
-    tl.skew = 0;
-    tl.hr_stride = g.Lh * site;
-    tl.stage_bytes = (tl.nslots * 2 * tl.hr_stride + 127) / 128 * 128;
+    tl.stage_bytes = (tl.nslots * 2 * g.Lh * site + 127) / 128 * 128;
     tl.nstages = (smem_limit - kSmemHeader - tl.units * 32 * 16 * (int)prec_bytes(precision)) / tl.stage_bytes;
     if (tl.nstages > 8) tl.nstages = 8;
     if (const char *e = getenv("MUGIQ_B200_FUSED_STAGES")) {

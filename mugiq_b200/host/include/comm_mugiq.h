@@ -1,0 +1,30 @@
+// comm_mugiq.h — multi-GPU plumbing of the C++ host mirror: one process per GPU, eigenvectors sharded over the ranks,
+// ONE NCCL all-reduce (sum) of the loop buffer over NVLink / NVSwitch.
+//
+// Replaces the reference's host-staged MPI_Reduce / MPI_Gather / MPI_Bcast of the momentum-space buffer
+// (/root/reference/lib/loop_mugiq.cpp:406-424) and its two MPI_Comm_split communicators (:62-88): there is no spatial
+// split to reduce over, the sum over eigenvector shards happens on the device buffer.  No MPI launcher exists in this
+// image, so ranks rendezvous through a file that rank 0 writes the ncclUniqueId to.
+#ifndef MUGIQ_B200_COMM_MUGIQ_H
+#define MUGIQ_B200_COMM_MUGIQ_H
+#include <cstddef>
+
+#include "mugiq_api.h"
+
+struct MugiqComm;  // opaque
+
+// Collective over all `size` ranks.  `device` is the CUDA device of this rank (cudaSetDevice is called).
+MugiqComm *mugiqCommInit(int rank, int size, int device, const char *id_file);
+void mugiqCommFinalize(MugiqComm *comm);
+int mugiqCommRank(const MugiqComm *comm);
+int mugiqCommSize(const MugiqComm *comm);
+// In-place sum of `count` real numbers of the given precision over all ranks (device buffer); returns when done.
+void mugiqCommAllReduceSum(MugiqComm *comm, void *buf_d, size_t count, QudaPrecision prec);
+// eigenvector shard [lo, hi) of rank r: contiguous blocks whose sizes differ by at most one
+void mugiqCommShard(int nEv, int rank, int size, int *lo, int *hi);
+
+// The communicator Loop_Mugiq sums its loop buffer over (nullptr = single process).
+void setLoopComm(MugiqComm *comm);
+MugiqComm *getLoopComm();
+
+#endif

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <fstream>
 
+#include "comm_mugiq.h"
 #include "host_util.h"
 
 template <typename Float, QudaFieldOrder fieldOrder> struct Loop_Mugiq<Float, fieldOrder>::LoopComputeParam {
@@ -229,9 +230,13 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   if (mugiq_b200_loop_plan_nloop(plan) != cPrm->nLoop) errorQuda("%s: plan holds %d loops, expected %d", __func__, mugiq_b200_loop_plan_nloop(plan), cPrm->nLoop);
 
   // eigenvectors are consumed in batches; QUDA-native orders are converted to the site-major layout batch by batch
-  const int batch = 32;
+  // Every batch costs one read-modify-write of the computed loop slots, so batches are as large as the kernel's
+  // pointer table allows (256); QUDA-native fields need a site-major staging copy, which is capped at 4 GiB.
   const size_t fieldBytes = eigsolve->eVecs[0]->Bytes();
   const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
+  int batch = 256;
+  if (native) batch = (int)std::max<size_t>(8, std::min<size_t>(256, ((size_t)4 << 30) / fieldBytes));
+  batch = std::min(batch, nEv);
   if (native && !evecStage_d) HOST_CUDA(cudaMalloc(&evecStage_d, fieldBytes * batch));
   std::vector<const void *> ptr(batch), src(batch);
   std::vector<void *> stage(batch);
@@ -253,6 +258,12 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   }
   MUGIQ_CHECK(mugiq_b200_loop_plan_finalize(plan, dataPos_d, 0, nullptr));
   if (!displace) mugiq_b200_loop_plan_destroy(plan);
+
+  // eigenvector shards (one process per GPU): sum the position-space buffer over the ranks on the device
+  if (getLoopComm() && mugiqCommSize(getLoopComm()) > 1) {
+    mugiqCommAllReduceSum(getLoopComm(), dataPos_d, (size_t)2 * nElemPosLoc, precision_of<Float>());
+    printfQuda("%s: Loop buffer summed over %d ranks\n", __func__, mugiqCommSize(getLoopComm()));
+  }
 
   // always copy the device position-space buffer to the host
   HOST_CUDA(cudaMemcpy(dataPos, dataPos_d, SizeCplxFloat * nElemPosLoc, cudaMemcpyDeviceToHost));

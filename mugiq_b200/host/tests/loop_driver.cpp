@@ -15,6 +15,7 @@
 #include <iostream>
 #include <map>
 
+#include "comm_mugiq.h"
 #include "host_util.h"
 #include "loop_mugiq.h"
 
@@ -64,19 +65,27 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
     gp.gauge_order = QUDA_QDP_GAUGE_ORDER;
     prm.gauge_param = &gp;
   }
+  // eigenvector shards: this rank keeps [lo, hi) of the file's eigenpairs
+  int lo = 0, hi = nEv;
+  if (getLoopComm()) mugiqCommShard(nEv, mugiqCommRank(getLoopComm()), mugiqCommSize(getLoopComm()), &lo, &hi);
+  if (hi <= lo) errorQuda("rank %d got an empty eigenvector shard (%d eigenvectors over %d ranks)", mugiqCommRank(getLoopComm()), nEv, mugiqCommSize(getLoopComm()));
+  {
+    std::vector<double> shard(sigma.begin() + lo, sigma.begin() + hi);
+    sigma.swap(shard);
+  }
   std::vector<ColorSpinorField *> fields;
   ColorSpinorParam cs;
   for (int i = 0; i < 4; i++) cs.x[i] = X[i];
   cs.precision = prec;
   cs.fieldOrder = order;
-  for (int n = 0; n < nEv; n++) {
+  for (int n = lo; n < hi; n++) {
     std::vector<char> one(ev.begin() + n * fieldBytes, ev.begin() + (n + 1) * fieldBytes);
     to_native<Float>(one, order, V4 / 2);
     fields.push_back(ColorSpinorField::Create(cs));
     HOST_CUDA(cudaMemcpy(fields.back()->V(), one.data(), fieldBytes, cudaMemcpyHostToDevice));
   }
   QudaEigParam qe;
-  qe.nEv = nEv;
+  qe.nEv = hi - lo;
   MugiqEigParam ep(&qe);
   Eigsolve_Mugiq eigsolve(&ep, fields, sigma);
 
@@ -153,9 +162,23 @@ int main(int argc, char **argv) {
     else if (opt["--field-order"] == "float4") order = QUDA_FLOAT4_FIELD_ORDER;
     else if (opt["--field-order"] != "site") errorQuda("Unknown --field-order %s", opt["--field-order"].c_str());
   }
+  // one process per GPU: --comm-size N --comm-rank r --comm-id-file f [--device d]
+  MugiqComm *comm = nullptr;
+  if (opt.count("--comm-size") && atoi(opt["--comm-size"].c_str()) > 1) {
+    if (!opt.count("--comm-rank") || !opt.count("--comm-id-file")) errorQuda("--comm-size needs --comm-rank and --comm-id-file");
+    const int rank = atoi(opt["--comm-rank"].c_str());
+    comm = mugiqCommInit(rank, atoi(opt["--comm-size"].c_str()), opt.count("--device") ? atoi(opt["--device"].c_str()) : rank,
+                         opt["--comm-id-file"].c_str());
+    setLoopComm(comm);
+  } else if (opt.count("--device")) {
+    HOST_CUDA(cudaSetDevice(atoi(opt["--device"].c_str())));
+  }
   const std::string prec = opt.count("--prec") ? opt["--prec"] : "double";
-  if (prec == "double") return run<double>(opt, X, prm, nEv, order);
-  if (prec == "single") return run<float>(opt, X, prm, nEv, order);
-  errorQuda("Unknown --prec %s (double/single)", prec.c_str());
-  return 1;
+  int rc = 1;
+  if (prec == "double") rc = run<double>(opt, X, prm, nEv, order);
+  else if (prec == "single") rc = run<float>(opt, X, prm, nEv, order);
+  else errorQuda("Unknown --prec %s (double/single)", prec.c_str());
+  setLoopComm(nullptr);
+  mugiqCommFinalize(comm);
+  return rc;
 }

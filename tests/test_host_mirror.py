@@ -115,6 +115,39 @@ def test_driver_matches_oracle(driver, oracle, tmp_path, order, prec):
 
 
 @pytest.mark.gpu
+def test_driver_eigenvector_shards_over_nccl(driver, oracle, tmp_path):
+    """Two driver processes, one per GPU, each with its eigenvector shard; the loop buffer is summed with one NCCL
+    all-reduce (comm_mugiq.h).  Every rank ends with the full result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL does not put two ranks on one device)")
+    from oracle import numpy_check as npc
+    from mugiq_b200.params import momenta_up_to
+    L, nEv = (4, 4, 4, 8), 7
+    ev, U, sig = _inputs(tmp_path, L, nEv, "double")
+    mom = momenta_up_to(1)
+    (tmp_path / "mom.txt").write_text("".join(f"{p[0]} {p[1]} {p[2]}\n" for p in mom))
+    entries = [(2, 1, 1, 2), (2, 0, 1, 2), (0, 0, 1, 1)]
+    procs = []
+    for rank in range(2):
+        args = [driver, "--dim", *L, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file", tmp_path / "sig.bin",
+                "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string", "+z:1,2;-z:1,2;-x:1",
+                "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--comm-size", 2, "--comm-rank", rank,
+                "--comm-id-file", tmp_path / "nccl.id", "--device", rank, "--dump-pos", tmp_path / f"pos{rank}.bin", "--dump-mom",
+                tmp_path / f"mom{rank}.bin"]
+        procs.append(subprocess.Popen([str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    ref_mom = npc.momentum_projection(ref, mom, -1, L)
+    for rank in range(2):
+        pos = np.fromfile(tmp_path / f"pos{rank}.bin", dtype=np.complex128).reshape(ref.shape)
+        dm = np.fromfile(tmp_path / f"mom{rank}.bin", dtype=np.complex128).reshape(ref_mom.shape)
+        assert rel_err(pos, ref) < TOL_F64 and rel_err(dm, ref_mom) < TOL_F64
+
+
+@pytest.mark.gpu
 def test_driver_public_entry_point_and_fatal_errors(driver, tmp_path):
     """computeLoop<Float>() through the registry (no dumps), then the reference's fatal paths: position-space writing is
     'Not supported yet', a precision mismatch aborts."""
