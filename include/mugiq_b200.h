@@ -142,6 +142,11 @@ int mugiq_b200_contract_batch(void *loop_d, const void *const *vL_d, const void 
  * covariantDisplacementVector_kernel (lib/mugiq_displace_kernels.cu:156-185). */
 int mugiq_b200_displace(void *dst_d, const void *src_d, const void *gauge_d, int dir, int sign,
                         const mugiq_b200_geom_t *geom, void *stream);
+/* The same hop for nvec fields in one launch (HOST arrays of device pointers): one link tile in shared memory serves
+ * the whole batch, 2S + U/nvec bytes per eigvec*site instead of 2S + U.  What Displace::doVectorDisplacement
+ * (lib/displace.cpp:55-67) does per eigenvector inside the loop nest lib/loop_mugiq.cpp:478-507, hoisted over n. */
+int mugiq_b200_displace_batch(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir,
+                              int sign, const mugiq_b200_geom_t *geom, void *stream);
 
 /* ---- stages 1+2 fused: the eigenvector loop of Loop_Mugiq::computeCoarseLoop -------------------- */
 /* For every eigenvector n and every loop iL (0 = ultra-local, then the entries in order, lengths

@@ -51,6 +51,7 @@ SYMBOLS = {
     "mugiq_b200_contract": (_i, [_vp, _vp, _vp, _d, _pg, _vp]),
     "mugiq_b200_contract_batch": (_i, [_vp, _pvp, _pvp, _pd, _i, _i, _pg, _vp]),
     "mugiq_b200_displace": (_i, [_vp, _vp, _vp, _i, _i, _pg, _vp]),
+    "mugiq_b200_displace_batch": (_i, [_pvp, _pvp, _i, _vp, _i, _i, _pg, _vp]),
     "mugiq_b200_loop_workspace_bytes": (_ll, [_pg, _i, _pe, _i]),
     "mugiq_b200_loop_accumulate": (_i, [_vp, _pvp, _pd, _i, _vp, _pe, _i, _i, _vp, _pg, _vp]),
     "mugiq_b200_loop_plan_create": (_i, [C.POINTER(_vp), _vp, _pe, _i, _pg, _vp]),

@@ -230,6 +230,24 @@ int mugiq_b200_displace(void *dst_d, const void *src_d, const void *gauge_d, int
   return displace(dst_d, src_d, gauge_d, dir, sign, g, geom->precision, (cudaStream_t)stream);
 }
 
+int mugiq_b200_displace_batch(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir,
+                              int sign, const mugiq_b200_geom_t *geom, void *stream) {
+  const char *who = "mugiq_b200_displace_batch";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  REQUIRE_PTR(dst_d, who);
+  REQUIRE_PTR(src_d, who);
+  REQUIRE_PTR(gauge_d, who);
+  if ((rc = check_dir_sign(dir, sign, who))) return rc;
+  if (nvec < 0) return set_error(MUGIQ_B200_EINVAL, "%s: nvec = %d", who, nvec);
+  for (int i = 0; i < nvec; i++) {
+    if (!dst_d[i] || !src_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: field %d is NULL", who, i);
+    if (dst_d[i] == src_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: dst and src of field %d must differ", who, i);
+  }
+  const LatGeom g = make_geom(geom->L);
+  return displace_batch(dst_d, src_d, nvec, gauge_d, dir, sign, g, geom->precision, (cudaStream_t)stream);
+}
+
 long long mugiq_b200_loop_workspace_bytes(const mugiq_b200_geom_t *geom, int nvec,
                                           const mugiq_b200_disp_entry_t *entries, int nentries) {
   const char *who = "mugiq_b200_loop_workspace_bytes";

@@ -9,13 +9,136 @@
 //    per eigenvector (lib/mugiq_contract_kernels.cu:120);
 //  * the gamma projection is applied once, after the eigenvector sum (it is linear), using only
 //    adds/swaps because every coefficient is +-1 or +-i (include/gamma.h:33-48).
+//
+// Two kernels: contract_tile_kernel streams 64-site tiles of every eigenvector (pair) of the batch through a
+// ring of shared-memory stages filled by bulk TMA (HBM-bound: S or 2S bytes and 192 DFMA per eigvec*site; the
+// per-thread strided 128-bit global loads of contract_site_kernel reached 70 % of the HBM peak);
+// contract_site_kernel serves fields that are not 16-byte aligned.
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace mugiq_b200 {
 
+constexpr int kCtrTile = 64;    // sites per CTA = threads per CTA
+constexpr int kCtrStages = 4;   // shared-memory stages (eigenvectors in flight per CTA: kCtrStages - 1)
+
+// out[(b+K)&3][(a+K)&3] = in[b][a]
+template <typename F, int K> __device__ __forceinline__ void unrotate_both(Cplx<F> M[4][4]) {
+  Cplx<F> T[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) T[(b + K) & 3][(a + K) & 3] = M[b][a];
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) M[b][a] = T[b][a];
+}
+
+// Thread = site.  The 192-byte site stride would put the 8 lanes of a quarter-warp on two 16-byte bank groups;
+// instead each lane reads its spins rotated by k = (lane/2) mod 4 (slot b holds spin (b+k) mod 4), which makes the
+// 128-bit shared reads conflict-free and only relabels M; the rotation is undone once after the eigenvector sum.
+template <typename F, bool kSame>
+__global__ void __launch_bounds__(kCtrTile)
+contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accumulate, const LatGeom g) {
+  extern __shared__ __align__(128) char smem[];
+  constexpr int kS = kSpinorLen * 2 * (int)sizeof(F);
+  constexpr int kC = 2 * (int)sizeof(F);
+  constexpr int kStage = (kSame ? 1 : 2) * kCtrTile * kS;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + kCtrStages * kStage);
+
+  const int site0 = blockIdx.x * kCtrTile;
+  const int nsites = min(kCtrTile, g.volume - site0);
+  const uint32_t bytes = (uint32_t)(nsites * kS);
+  const bool active = (int)threadIdx.x < nsites;
+  const int x_eo = site0 + threadIdx.x;
+
+  auto issue = [&](int n) {  // thread 0 only
+    const int slot = n % kCtrStages;
+    char *dst = smem + slot * kStage;
+    tma::mbar_expect_tx(&full[slot], kSame ? bytes : 2 * bytes);
+    tma::bulk_g2s(dst, static_cast<const char *>(batch.vL[n]) + (size_t)site0 * kS, bytes, &full[slot]);
+    if (!kSame) tma::bulk_g2s(dst + kCtrTile * kS, static_cast<const char *>(batch.vR[n]) + (size_t)site0 * kS, bytes, &full[slot]);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCtrStages; s++) tma::mbar_init(&full[s], 1);
+    tma::mbar_init_fence();
+    tma::fence_async_smem();
+    for (int n = 0; n < kCtrStages - 1 && n < batch.nvec; n++) issue(n);
+  }
+  __syncthreads();
+
+  Cplx<F> M[4][4];
+#pragma unroll
+  for (int be = 0; be < 4; be++)
+#pragma unroll
+    for (int al = 0; al < 4; al++) M[be][al] = make_c<F>(0, 0);
+
+  const int k = (threadIdx.x >> 1) & 3;
+  int off[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) off[b] = threadIdx.x * kS + ((b + k) & 3) * 3 * kC;
+
+  for (int n = 0; n < batch.nvec; n++) {
+    // slot of eigenvector n+S-1 was read in iteration n-1, before that iteration's barrier
+    if (threadIdx.x == 0 && n + kCtrStages - 1 < batch.nvec) issue(n + kCtrStages - 1);
+    const int slot = n % kCtrStages;
+    tma::mbar_wait(&full[slot], (uint32_t)((n / kCtrStages) & 1));
+    const char *st = smem + slot * kStage;
+    const F inv_sigma = (F)batch.inv_sigma[n];
+    Cplx<F> l[kSpinorLen], r[kSpinorLen];
+    if (active) {
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          l[b * 3 + c] = tma::lds_c<F>(st + off[b] + c * kC);
+          if (!kSame) r[b * 3 + c] = tma::lds_c<F>(st + kCtrTile * kS + off[b] + c * kC);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSpinorLen; i++) l[i] = r[i] = make_c<F>(0, 0);
+    }
+    __syncthreads();  // the stage may be refilled
+    if (kSame) {
+#pragma unroll
+      for (int i = 0; i < kSpinorLen; i++) r[i] = l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kSpinorLen; i++) {
+      l[i].re *= inv_sigma;
+      l[i].im *= inv_sigma;
+    }
+#pragma unroll
+    for (int be = 0; be < 4; be++)
+#pragma unroll
+      for (int al = 0; al < 4; al++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) cmac_conj(M[be][al], l[be * 3 + c], r[al * 3 + c]);
+  }
+  if (!active) return;
+  if (k == 1) unrotate_both<F, 1>(M);
+  if (k == 2) unrotate_both<F, 2>(M);
+  if (k == 3) unrotate_both<F, 3>(M);
+
+  Cplx<F> T[16];
+  gamma_project(T, M);
+#pragma unroll
+  for (int G = 0; G < 16; G++) {
+    F *p = loop + 2 * ((size_t)x_eo + (size_t)g.volume * G);
+    Cplx<F> out = T[G];
+    if (accumulate) {
+      const Cplx<F> old = ldg_c<F>(p);
+      out.re += old.re;
+      out.im += old.im;
+    }
+    st_c<F>(p, out);
+  }
+}
+
 template <typename F, bool kSame>
 __global__ void __launch_bounds__(128)
-contract_batch_kernel(F *__restrict__ loop, const VecBatch batch, const int accumulate, const LatGeom g) {
+contract_site_kernel(F *__restrict__ loop, const VecBatch batch, const int accumulate, const LatGeom g) {
   const int x_eo = blockIdx.x * blockDim.x + threadIdx.x;  // full-site index, parity-major
   if (x_eo >= g.volume) return;
 
@@ -68,6 +191,16 @@ contract_batch_kernel(F *__restrict__ loop, const VecBatch batch, const int accu
   }
 }
 
+template <typename F, bool kSame>
+static int launch_tile(void *loop_d, const VecBatch &batch, int accumulate, const LatGeom &g, cudaStream_t stream) {
+  const int smem = kCtrStages * (kSame ? 1 : 2) * kCtrTile * kSpinorLen * 2 * (int)sizeof(F) + kCtrStages * 8;
+  MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(contract_tile_kernel<F, kSame>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int blocks = (g.volume + kCtrTile - 1) / kCtrTile;
+  contract_tile_kernel<F, kSame><<<blocks, kCtrTile, smem, stream>>>((F *)loop_d, batch, accumulate, g);
+  MUGIQ_LAUNCH_CHECK();
+  return MUGIQ_B200_OK;
+}
+
 template <typename F>
 static int launch_contract(void *loop_d, const VecBatch &batch, bool same, int accumulate, const LatGeom &g,
                            cudaStream_t stream) {
@@ -75,11 +208,17 @@ static int launch_contract(void *loop_d, const VecBatch &batch, bool same, int a
   const int blocks = (g.volume + threads - 1) / threads;
   // algorithmic bytes: S (ultra-local) or 2S per eigvec·site, accumulator written once (+ read if accumulating)
   const double S = kSpinorLen * 2.0 * sizeof(F), A = 16 * 2.0 * sizeof(F);
-  ProfScope prof(K_CONTRACT, stream, (double)g.volume * (batch.nvec * (same ? S : 2 * S) + (accumulate ? 2 * A : A)));
+  ProfScope prof(K_CONTRACT, stream, (double)g.volume * (batch.nvec * (same ? S : 2 * S) + (accumulate ? 2 * A : A)),
+                 (double)g.volume * batch.nvec * 2.0 * (192 + 24));
+  bool aligned = true;  // bulk copies need 16-byte aligned fields
+  for (int i = 0; i < batch.nvec; i++)
+    if (((uintptr_t)batch.vL[i] | (uintptr_t)batch.vR[i]) & 15) aligned = false;
+  if (aligned) return same ? launch_tile<F, true>(loop_d, batch, accumulate, g, stream)
+                           : launch_tile<F, false>(loop_d, batch, accumulate, g, stream);
   if (same)
-    contract_batch_kernel<F, true><<<blocks, threads, 0, stream>>>((F *)loop_d, batch, accumulate, g);
+    contract_site_kernel<F, true><<<blocks, threads, 0, stream>>>((F *)loop_d, batch, accumulate, g);
   else
-    contract_batch_kernel<F, false><<<blocks, threads, 0, stream>>>((F *)loop_d, batch, accumulate, g);
+    contract_site_kernel<F, false><<<blocks, threads, 0, stream>>>((F *)loop_d, batch, accumulate, g);
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
 }

@@ -133,6 +133,18 @@ def displace(dst, src, gauge, direction, sign, L):
     return dst
 
 
+def displace_batch(dsts, srcs, gauge, direction, sign, L):
+    """One hop for a batch of fields in one launch (the link tile is loaded once per batch)."""
+    _dev(gauge, *dsts, *srcs)
+    n = len(srcs)
+    geom = make_geom(L, _prec(srcs[0]))
+    with torch.cuda.device(gauge.device):
+        check(_lib.load().mugiq_b200_displace_batch(ptr_array([d.data_ptr() for d in dsts]),
+                                                    ptr_array([s.data_ptr() for s in srcs]), n, gauge.data_ptr(),
+                                                    int(direction), int(sign), C.byref(geom), _stream()))
+    return dsts
+
+
 def loop_workspace_bytes(L, precision, nvec, entries):
     geom = make_geom(L, precision)
     return check(_lib.load().mugiq_b200_loop_workspace_bytes(C.byref(geom), nvec, entry_array(entries), len(entries)))

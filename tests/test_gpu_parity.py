@@ -69,6 +69,46 @@ def test_displace_all_directions(ops, oracle, L, prec):
             assert rel_err(host(out), oracle.displace(v, U, d, s, L)) < tol
 
 
+@pytest.mark.parametrize("L", [(16, 16, 2, 2), (24, 6, 2, 2), (6, 4, 2, 4), (8, 2, 2, 2), (32, 4, 1, 2)])
+@pytest.mark.parametrize("prec", [8, 4])
+def test_displace_batch_tiles(ops, oracle, L, prec):
+    """Batched hop on lattices whose y extent spans several tiles (wrap inside and across tiles), with odd Lx/2
+    (per-site kernel in FP32) and with more eigenvectors than pipeline stages; dst buffers are pre-filled with
+    garbage so that an unwritten site shows."""
+    n = 5
+    v = synth.random_evecs_np(L, n, seed=41).astype(cdt(prec))
+    U = synth.random_gauge(L, seed=41).astype(cdt(prec))
+    gd = ops.gauge_upload(U, L)
+    vd = [dev(v[i]) for i in range(n)]
+    tol = 1e-14 if prec == 8 else 1e-6
+    for d in range(4):
+        for s in (0, 1):
+            outs = [torch.full_like(vd[0], 7.0) for _ in range(n)]
+            ops.displace_batch(outs, vd, gd, d, s, L)
+            for i in range(n):
+                assert rel_err(host(outs[i]), oracle.displace(v[i], U, d, s, L)) < tol, (d, s, i)
+
+
+@pytest.mark.parametrize("L", [(6, 2, 2, 3), (2, 2, 2, 2), (16, 4, 4, 4)])
+@pytest.mark.parametrize("same", [True, False])
+def test_contract_batch_ragged_tiles(ops, oracle, L, same):
+    """Batched contraction with more eigenvectors than shared-memory stages and a last tile that is not full."""
+    n = 11
+    ev = synth.random_evecs_np(L, 2 * n, seed=43)
+    sig = [0.2 + 0.05 * i for i in range(n)]
+    V4 = ev.shape[1]
+    ref = np.zeros((16, V4), dtype=np.complex128)
+    for i in range(n):
+        ref = oracle.contract(ref, ev[i], ev[i] if same else ev[n + i], sig[i], L)
+    loop = torch.full((16, V4), 3.0, dtype=torch.complex128, device="cuda")
+    vl = [dev(ev[i]) for i in range(n)]
+    vr = None if same else [dev(ev[n + i]) for i in range(n)]
+    ops.contract_batch(loop, vl, vr, sig, L, accumulate=False)
+    assert rel_err(host(loop), ref) < TOL_F64
+    ops.contract_batch(loop, vl, vr, sig, L, accumulate=True)
+    assert rel_err(host(loop), 2 * ref) < TOL_F64
+
+
 def test_contract_batch_accumulate_and_overwrite(ops, oracle):
     L = (4, 4, 4, 8)
     n = 7
