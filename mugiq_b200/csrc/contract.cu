@@ -40,12 +40,12 @@ template <typename F, int K> __device__ __forceinline__ void unrotate_both(Cplx<
 // 128-bit shared reads conflict-free and only relabels M; the rotation is undone once after the eigenvector sum.
 template <typename F, bool kSame>
 __global__ void __launch_bounds__(kCtrTile)
-contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accumulate, const LatGeom g) {
+contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accumulate, const LatGeom g, const int nstages) {
   extern __shared__ __align__(128) char smem[];
   constexpr int kS = kSpinorLen * 2 * (int)sizeof(F);
   constexpr int kC = 2 * (int)sizeof(F);
   constexpr int kStage = (kSame ? 1 : 2) * kCtrTile * kS;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + kCtrStages * kStage);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + nstages * kStage);  // nstages = min(kCtrStages, nvec)
 
   const int site0 = blockIdx.x * kCtrTile;
   const int nsites = min(kCtrTile, g.volume - site0);
@@ -53,18 +53,23 @@ contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accum
   const bool active = (int)threadIdx.x < nsites;
   const int x_eo = site0 + threadIdx.x;
 
-  auto issue = [&](int n) {  // thread 0 only
-    const int slot = n % kCtrStages;
+  auto issue = [&](int n, int slot) {  // thread 0 only
     char *dst = smem + slot * kStage;
     tma::mbar_expect_tx(&full[slot], kSame ? bytes : 2 * bytes);
     tma::bulk_g2s(dst, static_cast<const char *>(batch.vL[n]) + (size_t)site0 * kS, bytes, &full[slot]);
     if (!kSame) tma::bulk_g2s(dst + kCtrTile * kS, static_cast<const char *>(batch.vR[n]) + (size_t)site0 * kS, bytes, &full[slot]);
   };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kCtrStages; s++) tma::mbar_init(&full[s], 1);
+    for (int s = 0; s < nstages; s++) tma::mbar_init(&full[s], 1);
     tma::mbar_init_fence();
     tma::fence_async_smem();
-    for (int n = 0; n < kCtrStages - 1 && n < batch.nvec; n++) issue(n);
+    for (int n = 0; n < nstages - 1 || n == 0; n++) issue(n, n);  // nstages <= nvec
+  }
+  // accumulating call (performLoopContraction is one): fetch the old loop values while the first stage is in flight
+  Cplx<F> old[16];
+  if (accumulate && active) {
+#pragma unroll
+    for (int G = 0; G < 16; G++) old[G] = ldg_c<F>(loop + 2 * ((size_t)x_eo + (size_t)g.volume * G));
   }
   __syncthreads();
 
@@ -79,11 +84,12 @@ contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accum
 #pragma unroll
   for (int b = 0; b < 4; b++) off[b] = threadIdx.x * kS + ((b + k) & 3) * 3 * kC;
 
+  int slot = 0, pslot = nstages - 1;  // slot of eigenvector n, slot of eigenvector n + nstages - 1
+  uint32_t par = 0;
   for (int n = 0; n < batch.nvec; n++) {
-    // slot of eigenvector n+S-1 was read in iteration n-1, before that iteration's barrier
-    if (threadIdx.x == 0 && n + kCtrStages - 1 < batch.nvec) issue(n + kCtrStages - 1);
-    const int slot = n % kCtrStages;
-    tma::mbar_wait(&full[slot], (uint32_t)((n / kCtrStages) & 1));
+    // the slot of eigenvector n+S-1 was read in iteration n-1, before that iteration's barrier
+    if (threadIdx.x == 0 && nstages > 1 && n + nstages - 1 < batch.nvec) issue(n + nstages - 1, pslot);
+    tma::mbar_wait(&full[slot], par);
     const char *st = smem + slot * kStage;
     const F inv_sigma = (F)batch.inv_sigma[n];
     Cplx<F> l[kSpinorLen], r[kSpinorLen];
@@ -115,6 +121,11 @@ contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accum
       for (int al = 0; al < 4; al++)
 #pragma unroll
         for (int c = 0; c < 3; c++) cmac_conj(M[be][al], l[be * 3 + c], r[al * 3 + c]);
+    if (++slot == nstages) {
+      slot = 0;
+      par ^= 1u;
+    }
+    if (++pslot == nstages) pslot = 0;
   }
   if (!active) return;
   if (k == 1) unrotate_both<F, 1>(M);
@@ -128,9 +139,8 @@ contract_tile_kernel(F *__restrict__ loop, const VecBatch batch, const int accum
     F *p = loop + 2 * ((size_t)x_eo + (size_t)g.volume * G);
     Cplx<F> out = T[G];
     if (accumulate) {
-      const Cplx<F> old = ldg_c<F>(p);
-      out.re += old.re;
-      out.im += old.im;
+      out.re += old[G].re;
+      out.im += old[G].im;
     }
     st_c<F>(p, out);
   }
@@ -193,10 +203,11 @@ contract_site_kernel(F *__restrict__ loop, const VecBatch batch, const int accum
 
 template <typename F, bool kSame>
 static int launch_tile(void *loop_d, const VecBatch &batch, int accumulate, const LatGeom &g, cudaStream_t stream) {
-  const int smem = kCtrStages * (kSame ? 1 : 2) * kCtrTile * kSpinorLen * 2 * (int)sizeof(F) + kCtrStages * 8;
+  const int nstages = batch.nvec < kCtrStages ? batch.nvec : kCtrStages;  // a single pair leaves room for more CTAs per SM
+  const int smem = nstages * (kSame ? 1 : 2) * kCtrTile * kSpinorLen * 2 * (int)sizeof(F) + kCtrStages * 8;
   MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(contract_tile_kernel<F, kSame>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int blocks = (g.volume + kCtrTile - 1) / kCtrTile;
-  contract_tile_kernel<F, kSame><<<blocks, kCtrTile, smem, stream>>>((F *)loop_d, batch, accumulate, g);
+  contract_tile_kernel<F, kSame><<<blocks, kCtrTile, smem, stream>>>((F *)loop_d, batch, accumulate, g, nstages);
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
 }

@@ -25,34 +25,62 @@ struct PosGeom {
   int Lt, V3h, nLoop, N;
   long long Vh, V4;
   long long M;  // Lt * 16 * nLoop
-  int kchunk, nchunk;  // chunk of the V3/2 run handled by one task; chunks per run
+  int kchunk, nchunk;  // chunk of the V3/2 run handled by one task (multiple of kPosKT); chunks per run
+  // DMMA kernel: row groups (t, iL) are binned by class c = 2*parity + s, s = (t + parity) & 1, so that the warps of a
+  // CTA share one phase operand; class c owns CTAs [blk0[c], blk0[c+1]) x nchunk
+  int nT[2];    // time-slices with t & 1 == 0 / 1
+  int blk0[5];
 };
 
+// GammaMap as a bit mask / closed form, for kernels that index it with a runtime G (a constexpr table indexed at run
+// time lands in local memory); verified against the literal tables of common.cuh at compile time.
+constexpr unsigned kMapMinusMask = (1u << 3) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 14);
+constexpr bool map_mask_matches_tables() {
+  constexpr GammaTables t = gamma_tables();
+  for (int G = 0; G < 16; G++)
+    if (t.map_index[G] != 15 - G || (t.map_sign[G] < 0) != (((kMapMinusMask >> G) & 1) != 0)) return false;
+  return true;
+}
+static_assert(map_mask_matches_tables(), "gamma map mask out of sync with gamma_tables()");
+
+constexpr int kPosKT = 16;     // sites of the K run per shared-memory phase tile (4 DMMA k-steps)
+constexpr int kPosWarps = 4;   // warps (= row groups of 16 gammas) per CTA
+
 __device__ __forceinline__ void dmma_m8n8k4_pos(double &c0, double &c1, const double a, const double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
-// one warp = one task (t, iL, parity, chunk); NT = number of 4-momentum tiles
+// CTA = kPosWarps row groups (t, iL) of one class (same parity, same s => same phase rows) x one K chunk; warp = the 16
+// gammas of one row group for NT*4 momenta.  The phase operand of a K tile is staged in shared memory once per CTA,
+// already in the real embedding the A fragment needs ((re, -im) for the real rows of the result, (im, re) for the
+// imaginary ones: one conflict-free 128-bit read per 4 DMMAs, no selects); the dataPos operand has no reuse and goes
+// straight from global memory into the B fragments, one K tile ahead of the tensor pipe.
 template <int NT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kPosWarps * 32, (NT <= 4 ? 4 : 2))
 momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__ pos, const double *__restrict__ P,
-                        const PosGeom pg, const int n0_base) {
-  constexpr GammaTables gt = gamma_tables();
-  const int lane = threadIdx.x & 31;
-  const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long ntask = (long long)pg.Lt * pg.nLoop * 2 * pg.nchunk;
-  if (task >= ntask) return;
-  const int chunk = (int)(task % pg.nchunk);
-  const int p = (int)((task / pg.nchunk) & 1);
-  const long long pair = task / (2 * pg.nchunk);
-  const int t = (int)(pair % pg.Lt), iL = (int)(pair / pg.Lt);
-  const int s = (t + p) & 1;
+                        const PosGeom pg, const int n0) {
+  constexpr int kThreads = kPosWarps * 32;
+  constexpr int kElems = NT * 4 * kPosKT;                  // complex phases per tile
+  constexpr int kPer = (kElems + kThreads - 1) / kThreads;  // per thread
+  __shared__ __align__(128) double ph_s[2][NT * 4][kPosKT][4];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int b = blockIdx.x;
+  const int chunk = b % pg.nchunk;
+  b /= pg.nchunk;
+  const int c = (b >= pg.blk0[1]) + (b >= pg.blk0[2]) + (b >= pg.blk0[3]);
+  const int p = c >> 1, s = c & 1, tbit = s ^ p;
+  const int nT = tbit ? pg.nT[1] : pg.nT[0];
+  const int cb0 = c == 0 ? pg.blk0[0] : c == 1 ? pg.blk0[1] : c == 2 ? pg.blk0[2] : pg.blk0[3];
+  const int r = (b - cb0) * kPosWarps + warp;
+  const bool active = r < nT * pg.nLoop;  // warp-uniform
+  const int iL = active ? r / nT : 0;
+  const int t = active ? 2 * (r - iL * nT) + tbit : tbit;
   const int gi = lane >> 2, j = lane & 3, comp = gi & 1;
-  const int kbeg = chunk * pg.kchunk;
-  const int kend = min(pg.V3h, kbeg + pg.kchunk);
-  const int n0 = n0_base;
+  const int tile0 = chunk * (pg.kchunk / kPosKT);
+  const int tile1 = min((pg.V3h + kPosKT - 1) / kPosKT, tile0 + pg.kchunk / kPosKT);
 
   double acc[2][NT][2];
 #pragma unroll
@@ -60,36 +88,75 @@ momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-  // row of gamma G = mt*8 + gi: sites of (t, parity) start at p*Vh + t*V3h
+  // row of gamma G = mt*8 + gi: the sites of (t, parity) start at p*Vh + t*V3h
   const double2 *arow[2];
 #pragma unroll
   for (int mt = 0; mt < 2; mt++)
     arow[mt] = reinterpret_cast<const double2 *>(pos) + ((long long)p * pg.Vh + (long long)t * pg.V3h) +
                pg.V4 * ((mt * 8 + gi) + 16LL * iL);
-  const double2 *prow[NT];
+  const double2 *P2 = reinterpret_cast<const double2 *>(P) + (long long)s * pg.N * pg.V3h;
+
+  double2 phr[kPer];
+  auto ph_load = [&](int tile) {
 #pragma unroll
-  for (int nt = 0; nt < NT; nt++) {
-    const int n = n0 + nt * 4 + (gi >> 1);
-    prow[nt] = reinterpret_cast<const double2 *>(P) + ((long long)s * pg.N + (n < pg.N ? n : 0)) * pg.V3h;
-  }
-  for (int k0 = kbeg; k0 < kend; k0 += 4) {
-    const int k = k0 + j;
-    const bool kok = k < kend;
-    double2 d[2];
+    for (int i = 0; i < kPer; i++) {
+      const int e = tid + i * kThreads;
+      const int n = n0 + e / kPosKT, k = tile * kPosKT + (e % kPosKT);
+      phr[i] = (e < kElems && n < pg.N && k < pg.V3h) ? __ldg(P2 + (long long)n * pg.V3h + k) : make_double2(0.0, 0.0);
+    }
+  };
+  auto ph_store = [&](int buf) {
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++) d[mt] = kok ? __ldg(arow[mt] + k) : make_double2(0.0, 0.0);
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-      const int n = n0 + nt * 4 + (gi >> 1);
-      const double2 pz = (kok && n < pg.N) ? __ldg(prow[nt] + k) : make_double2(0.0, 0.0);
-      const double a1 = comp ? pz.y : pz.x, a2 = comp ? pz.x : -pz.y;
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        dmma_m8n8k4_pos(acc[mt][nt][0], acc[mt][nt][1], a1, d[mt].x);
-        dmma_m8n8k4_pos(acc[mt][nt][0], acc[mt][nt][1], a2, d[mt].y);
+    for (int i = 0; i < kPer; i++) {
+      const int e = tid + i * kThreads;
+      if (e < kElems) {
+        double2 *d = reinterpret_cast<double2 *>(&ph_s[buf][e / kPosKT][e % kPosKT][0]);
+        d[0] = make_double2(phr[i].x, -phr[i].y);
+        d[1] = make_double2(phr[i].y, phr[i].x);
       }
     }
+  };
+  double2 aT[4][2], aN[4][2];
+  auto a_load = [&](double2 (&a)[4][2], int tile) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int k = tile * kPosKT + ks * 4 + j;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) a[ks][mt] = (active && k < pg.V3h) ? __ldg(arow[mt] + k) : make_double2(0.0, 0.0);
+    }
+  };
+
+  ph_load(tile0);
+  a_load(aT, tile0);
+  ph_store(0);
+  __syncthreads();
+  for (int tile = tile0; tile < tile1; tile++) {
+    const int buf = (tile - tile0) & 1;
+    const bool more = tile + 1 < tile1;
+    if (more) {
+      ph_load(tile + 1);
+      a_load(aN, tile + 1);
+    }
+    if (active) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          const double2 a = *reinterpret_cast<const double2 *>(&ph_s[buf][nt * 4 + (gi >> 1)][ks * 4 + j][comp * 2]);
+          dmma_m8n8k4_pos(acc[0][nt][0], acc[0][nt][1], a.x, aT[ks][0].x);
+          dmma_m8n8k4_pos(acc[1][nt][0], acc[1][nt][1], a.x, aT[ks][1].x);
+          dmma_m8n8k4_pos(acc[0][nt][0], acc[0][nt][1], a.y, aT[ks][0].y);
+          dmma_m8n8k4_pos(acc[1][nt][0], acc[1][nt][1], a.y, aT[ks][1].y);
+        }
+    }
+    if (more) ph_store(buf ^ 1);
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) aT[ks][mt] = aN[ks][mt];
   }
+  if (!active) return;
   // c-fragment: row gi -> (n, comp); columns 2j, 2j+1 -> gamma G = mt*8 + 2j + e.  Written under the mapped index.
   double *out = partial + 2 * (size_t)(p * pg.nchunk + chunk) * (size_t)pg.M * pg.N;
 #pragma unroll
@@ -100,9 +167,9 @@ momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__
       if (n < pg.N) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          const int G = mt * 8 + 2 * j + e;
-          const long long m = t + (long long)pg.Lt * (gt.map_index[G] + 16 * iL);
-          out[2 * (m + pg.M * n) + comp] = (double)gt.map_sign[G] * acc[mt][nt][e];
+          const int G = mt * 8 + 2 * j + e;  // runtime index: use the bit-mask form of the map tables (checked below)
+          const long long m = t + (long long)pg.Lt * ((15 - G) + 16 * iL);
+          out[2 * (m + pg.M * n) + comp] = ((kMapMinusMask >> G) & 1) ? -acc[mt][nt][e] : acc[mt][nt][e];
         }
       }
     }
@@ -224,16 +291,34 @@ static PosGeom make_pos_geom(const LatGeom &g, int nLoop, int N) {
   pg.Vh = g.volumeCB;
   pg.V4 = g.volume;
   pg.M = (long long)g.L[3] * 16 * nLoop;
-  // enough tasks to fill the GPU (148 SMs x 32 warps), at least 64 sites per chunk, at most 16 chunks per run
-  const long long pairs = (long long)pg.Lt * nLoop * 2;
-  long long want = (148LL * 32 + pairs - 1) / pairs;
-  long long maxc = pg.V3h / 64;
-  if (maxc < 1) maxc = 1;
-  if (want > maxc) want = maxc;
-  if (want > 16) want = 16;
-  if (want < 1) want = 1;
-  pg.kchunk = (int)(((pg.V3h + want - 1) / want + 3) / 4 * 4);
-  pg.nchunk = (pg.V3h + pg.kchunk - 1) / pg.kchunk;
+  // CTAs of the DMMA kernel: classes c = 2*parity + s hold the time-slices with t & 1 == s ^ parity
+  pg.nT[0] = (pg.Lt + 1) / 2;
+  pg.nT[1] = pg.Lt / 2;
+  pg.blk0[0] = 0;
+  for (int c = 0; c < 4; c++) {
+    const int nR = pg.nT[(c & 1) ^ (c >> 1)] * nLoop;
+    pg.blk0[c + 1] = pg.blk0[c] + (nR + kPosWarps - 1) / kPosWarps;
+  }
+  // split of the V3/2 run: whole tiles, at least 4 tiles per chunk, at most 16 chunks; the count that fills the 148 SMs
+  // most evenly (CTAs resident per SM: 4 for <= 16 momenta, 2 above), fewer chunks preferred (less split-K traffic)
+  const int ntiles = (pg.V3h + kPosKT - 1) / kPosKT;
+  const int slots = 148 * (std::min(N, 36) <= 16 ? 4 : 2);
+  int best = 1;
+  double best_score = -1.0;
+  for (int nc = 1; nc <= 16 && nc * 4 <= std::max(ntiles, 4); nc++) {
+    const int tpc = (ntiles + nc - 1) / nc;
+    const int real_nc = (ntiles + tpc - 1) / tpc;
+    const long long ctas = (long long)pg.blk0[4] * real_nc;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double score = (double)ctas / (double)(waves * slots) - 0.004 * real_nc;
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = real_nc;
+    }
+  }
+  const int tpc = (ntiles + best - 1) / best;
+  pg.kchunk = tpc * kPosKT;
+  pg.nchunk = (ntiles + tpc - 1) / tpc;
   return pg;
 }
 
@@ -251,7 +336,7 @@ int momproj_pos(void *mom_d, const void *pos_d, const void *phase_eo_d, int nLoo
   {
     ProfScope prof(K_MOMPROJ, stream, bytes, 8.0 * (double)pg.M * N * (double)g.V3);
     if (precision == MUGIQ_B200_PREC_DOUBLE) {
-      const int blocks = (int)((ntask + 3) / 4);
+      const int blocks = pg.blk0[4] * pg.nchunk;
       const double *A = (const double *)pos_d, *P = (const double *)phase_eo_d;
       double *ws = (double *)workspace_d;
       // momenta in passes of up to 36 (9 tiles of 4): A is re-read once per pass
@@ -259,10 +344,10 @@ int momproj_pos(void *mom_d, const void *pos_d, const void *phase_eo_d, int nLoo
         const int nt = (std::min(N - n0, 36) + 3) / 4;
         switch (nt) {
 #define MUGIQ_NT_CASE(k) \
-  case k: momproj_pos_dmma_kernel<k><<<blocks, 128, 0, stream>>>(ws, A, P, pg, n0); break;
+  case k: momproj_pos_dmma_kernel<k><<<blocks, kPosWarps * 32, 0, stream>>>(ws, A, P, pg, n0); break;
           MUGIQ_NT_CASE(9) MUGIQ_NT_CASE(8) MUGIQ_NT_CASE(7) MUGIQ_NT_CASE(6) MUGIQ_NT_CASE(5)
           MUGIQ_NT_CASE(4) MUGIQ_NT_CASE(3) MUGIQ_NT_CASE(2)
-          default: momproj_pos_dmma_kernel<1><<<blocks, 128, 0, stream>>>(ws, A, P, pg, n0); break;
+          default: momproj_pos_dmma_kernel<1><<<blocks, kPosWarps * 32, 0, stream>>>(ws, A, P, pg, n0); break;
 #undef MUGIQ_NT_CASE
         }
         MUGIQ_LAUNCH_CHECK();

@@ -10,83 +10,77 @@ namespace mugiq_b200 {
 // ---------------------------------------------------------------------------------------------------
 // Reorder:  out[t + Lt*((15-G) + 16*iL) + Lt*nData*v3] = sign[G] * in[x_eo + V4*(G + 16*iL)]
 //
-// The input is contiguous in x_eo for fixed (G,iL); the output is contiguous in t for fixed (G',iL,v3)
-// and then in idata.  A CTA owns kTileV (<= 16) spatial sites (consecutive v3) and all Lt time-slices for a chunk
-// of kTileD data columns: it gathers in[.] (coalesced along x within a lattice row) into a shared
-// [v3][idata][t] tile and writes runs of kTileD*Lt contiguous complex numbers per spatial site.
-// The reference writes each element with stride Lt*nData between neighbouring x
+// Pure data movement (512 B per site and loop in FP64).  The input is contiguous in x_eo for fixed (G, iL): for a
+// tile of R consecutive-y lattice rows the sites of one (t, parity) are ONE run of R*Lx/2 complex numbers; the output
+// is contiguous in t for fixed (G', iL, v3).  A CTA owns one (G, iL) and one tile of rows for all t: it reads
+// 2*Lt runs (a warp per run, lanes along the run), transposes through a padded shared tile indexed
+// [parity][position in run][t] (conflict-free both ways: odd row stride, and the parity of a site alternates with t
+// while its position in the run does not) and writes Lt consecutive complex numbers per site (a warp per site, lanes
+// along t).  The reference writes each element with stride Lt*nData between neighbouring x
 // (lib/mugiq_util_kernels.cu:92-96).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kTileD = 16;  // idata columns per CTA (one loop's 16 gammas)
-
 template <typename F>
 __global__ void __launch_bounds__(256)
-reorder_mapgamma_kernel(F *__restrict__ out, const F *__restrict__ in, const int nLoop, const int kTileV,
-                        const LatGeom g) {
+reorder_mapgamma_kernel(F *__restrict__ out, const F *__restrict__ in, const int nLoop, const int R, const LatGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Cplx<F> *tile = reinterpret_cast<Cplx<F> *>(smem_raw);  // [kTileV][kTileD][Lt (+1 pad)]
+  Cplx<F> *tile = reinterpret_cast<Cplx<F> *>(smem_raw);  // [2][R*Lh][Lt | 1]
   constexpr GammaTables gt = gamma_tables();
-  const int Lt = g.L[3];
-  const int Ltp = Lt + 1;
+  const int Lt = g.L[3], Ltp = Lt | 1;
+  const int NS = R * g.Lh;  // sites of the tile per parity
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int row0 = blockIdx.x * R;  // first row y + Ly*z of the tile
+  const int idata = blockIdx.y, G = idata & 15, iL = idata >> 4;
   const int nData = 16 * nLoop;
-  const int v3_0 = blockIdx.x * kTileV;
-  const int iL = blockIdx.y;
+  F sgn = 1;
+  int Gp = 0;
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    if (q == G) {
+      sgn = (F)gt.map_sign[q];
+      Gp = gt.map_index[q];
+    }
 
-  // gather: element e -> (G, t, dv) with dv fastest so that reads run along x
-  const int nElem = kTileD * Lt * kTileV;
-  for (int e = threadIdx.x; e < nElem; e += blockDim.x) {
-    const int dv = e % kTileV;
-    const int t = (e / kTileV) % Lt;
-    const int G = e / (kTileV * Lt);
-    const int v3 = v3_0 + dv;
-    if (v3 < g.V3) {
-      const int xx = v3 % g.L[0];
-      const int yz = v3 / g.L[0];
-      const int yy = yz % g.L[1];
-      const int zz = yz / g.L[1];
-      const int pty = (xx + yy + zz + t) & 1;
-      const int x_cb = (v3 + g.V3 * t) >> 1;
-      const size_t x_eo = (size_t)x_cb + (size_t)pty * g.volumeCB;
-      Cplx<F> z = ldg_c<F>(in + 2 * (x_eo + (size_t)g.volume * (G + 16 * iL)));
-      const F sgn = (F)gt.map_sign[G];
+  const F *src = in + 2 * ((size_t)g.volume * idata + (size_t)row0 * g.Lh);
+  for (int tp = warp; tp < 2 * Lt; tp += nwarp) {
+    const int t = tp >> 1, pty = tp & 1;
+    const F *run = src + 2 * ((size_t)pty * g.volumeCB + (size_t)t * (g.V3 >> 1));
+    for (int i = lane; i < NS; i += 32) {
+      Cplx<F> z = ldg_c<F>(run + 2 * i);
       z.re *= sgn;
       z.im *= sgn;
-      tile[(dv * kTileD + gt.map_index[G]) * Ltp + t] = z;
+      tile[(pty * NS + i) * Ltp + t] = z;
     }
   }
   __syncthreads();
-  // scatter: for each spatial site a run of kTileD*Lt contiguous outputs
-  const int run = kTileD * Lt;
-  for (int e = threadIdx.x; e < run * kTileV; e += blockDim.x) {
-    const int r = e % run;
-    const int dv = e / run;
-    const int v3 = v3_0 + dv;
-    if (v3 < g.V3) {
-      const int t = r % Lt;
-      const int Gp = r / Lt;
-      const size_t o = (size_t)t + (size_t)Lt * (Gp + 16 * iL) + (size_t)Lt * nData * v3;
-      st_c<F>(out + 2 * o, tile[(dv * kTileD + Gp) * Ltp + t]);
-    }
+  const int yz0 = (row0 % g.L[1]) + (row0 / g.L[1]);  // y + z of the first row (parity only)
+  for (int ls = warp; ls < R * g.L[0]; ls += nwarp) {
+    const int a = ls / g.L[0], x = ls - a * g.L[0];
+    const int i = ls >> 1;                      // position in the run: (a*Lx + x) >> 1
+    const int c = (x + yz0 + a) & 1;            // parity of the site at t = 0
+    const size_t v3 = (size_t)(row0 + a) * g.L[0] + x;
+    F *dst = out + 2 * ((size_t)Lt * (Gp + 16 * iL) + (size_t)Lt * nData * v3);
+    for (int t = lane; t < Lt; t += 32) st_c<F>(dst + 2 * t, tile[((((c + t) & 1) * NS) + i) * Ltp + t]);
   }
 }
 
 int reorder_mapgamma(void *out_d, const void *in_d, int nLoop, const LatGeom &g, int precision, cudaStream_t stream) {
-  // spatial sites per CTA: as many as fit a ~96 KB tile, at most 16
-  const size_t per_site = (size_t)kTileD * (g.L[3] + 1) * 2 * prec_bytes(precision);
-  int kTileV = (int)((96 * 1024) / per_site);
-  if (kTileV > 16) kTileV = 16;
-  if (kTileV < 1) return set_error(MUGIQ_B200_EINVAL, "reorder_mapgamma: Lt=%d too large for the tile", g.L[3]);
-  const dim3 grid((g.V3 + kTileV - 1) / kTileV, nLoop);
-  const size_t smem = (size_t)kTileV * per_site;
+  // rows per tile: R | Ly with R*Lx/2 <= 32 (one warp-wide read per run), shrunk if the tile exceeds 64 KB
+  const size_t per_row = (size_t)2 * g.Lh * (g.L[3] | 1) * 2 * prec_bytes(precision);
+  int R = 1;
+  for (int r = 1; r <= g.L[1]; r++)
+    if (g.L[1] % r == 0 && r * g.Lh <= 32 && r * per_row <= 64 * 1024) R = r;
+  const size_t smem = (size_t)R * per_row;
+  if (smem > 200 * 1024) return set_error(MUGIQ_B200_EINVAL, "reorder_mapgamma: Lx*Lt = %d*%d too large for the tile", g.L[0], g.L[3]);
+  const dim3 grid(g.L[1] * g.L[2] / R, 16 * nLoop);
   ProfScope prof(K_REORDER, stream, 2.0 * 16.0 * nLoop * (double)g.volume * 2.0 * prec_bytes(precision));
   if (precision == MUGIQ_B200_PREC_DOUBLE) {
     MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(reorder_mapgamma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-    reorder_mapgamma_kernel<double><<<grid, 256, smem, stream>>>((double *)out_d, (const double *)in_d, nLoop, kTileV, g);
+    reorder_mapgamma_kernel<double><<<grid, 256, smem, stream>>>((double *)out_d, (const double *)in_d, nLoop, R, g);
   } else {
     MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(reorder_mapgamma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-    reorder_mapgamma_kernel<float><<<grid, 256, smem, stream>>>((float *)out_d, (const float *)in_d, nLoop, kTileV, g);
+    reorder_mapgamma_kernel<float><<<grid, 256, smem, stream>>>((float *)out_d, (const float *)in_d, nLoop, R, g);
   }
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
