@@ -4,14 +4,21 @@
 // used by tests/, by __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs as the
 // checker and as the timed host baseline, never as the product path.
 //
-// *** PARITY UNPINNED. ***  The reference (ckallidonis/mugiq) ships no unit tests, golden vectors or
-// fixtures for this path and cannot be built here: every hot-path translation unit
-// includes QUDA headers (include/contract_util.cuh:6-10) and QUDA is neither vendored nor installed
-// (version unpinned: CMake takes MUGIQ_QUDA_HOME only, CMakeLists.txt:112-114).  This file therefore
-// restates the reference's kernels from their source, and restates the few QUDA semantics they rely on
-// from QUDA's public definitions (assumptions A1-A5 below).  It is pinned only by the algebraic
-// known-answer tests of tests/test_oracle_kats.py and by an independent numpy
-// restatement (oracle/numpy_check.py).
+// *** PARITY: PINNED TO THE REFERENCE'S KERNEL CODE, QUDA'S ACCESSORS ASSUMED. ***  The reference (ckallidonis/mugiq)
+// ships no unit tests, golden vectors or fixtures for this path, and its full path cannot be
+// built here: QUDA is neither vendored nor installed (version unpinned: CMake takes MUGIQ_QUDA_HOME only,
+// CMakeLists.txt:112-114).  What CAN be built is the reference's own kernel layer: lib/contract_wrappers.cu and
+// lib/mugiq_{contract,displace,util}_kernels.cu compile UNMODIFIED against a small restatement of the QUDA interfaces
+// they touch (oracle/quda_shim/, `make -C oracle ref` -> oracle/_ref/libmugiq_ref.so).  This file is checked against
+//   (a) golden vectors those reference kernels produced on a B200 (tests/golden/ref_kernels_4x4x4x8.npz, generator
+//       tests/golden/make_ref_golden.py; CPU suite tests/test_golden_ref.py),
+//   (b) the same kernels live on the GPU box (tests/test_ref_kernels.py, which also compares the product's kernels
+//       with them directly),
+//   (c) the algebraic known-answer tests of tests/test_oracle_kats.py and an independent numpy
+//       restatement (oracle/numpy_check.py).
+// So the kernel arithmetic, the gamma tables and their assembly, which neighbour / link / parity / dagger a displacement
+// picks, the reorder index and sign map and the phase formula are pinned to the reference's code; the QUDA semantics
+// A1-A5 below (shared by this file and by the shim) remain assumptions, restated from QUDA's public definitions.
 //
 // QUDA semantics assumed (github.com/lattice/quda, develop of early 2020):
 //  A1 getCoords(x, cb, X, parity): za=cb/(X0/2); zb=za/X1; x1=za-zb*X1; x3=zb/X2; x2=zb-x3*X2;

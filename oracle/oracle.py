@@ -1,6 +1,7 @@
 """ctypes front end of oracle/liboracle_mugiq.so (the CPU restatement in mugiq_oracle.cpp).
 
-TEST INFRASTRUCTURE ONLY — parity unpinned (the reference has no golden vectors; see mugiq_oracle.cpp).
+TEST INFRASTRUCTURE ONLY.  Pinned by golden vectors of the reference's own CUDA kernels (tests/golden/ref_kernels_*.npz,
+oracle/ref_kernels.py); QUDA's accessor conventions remain assumptions (see the header of mugiq_oracle.cpp).
 All arrays are numpy, complex128 or complex64, in the same memory orders the C-ABI uses."""
 import ctypes as C
 import os

@@ -1,0 +1,3 @@
+// color_spinor_field.h — see quda_shim_core.h (oracle/ test infrastructure: QUDA is not installed in this image)
+#pragma once
+#include "quda_shim_core.h"

@@ -1,0 +1,185 @@
+// ref_driver.cu — TEST INFRASTRUCTURE (oracle/): C-ABI around the reference's OWN CUDA wrappers and kernels
+// (/root/reference/lib/contract_wrappers.cu + lib/mugiq_{contract,displace,util}_kernels.cu, compiled unmodified
+// against oracle/quda_shim/, see the header of quda_shim_core.h for what the shim assumes about QUDA).
+// Only tests/, __graft_entry__.smoke() and bench.py's reference legs load the resulting oracle/_ref/libmugiq_ref.so.
+//
+// mugiq_ref_loop restates the eigenvector x displacement loop nest of Loop_Mugiq::computeCoarseLoop
+// (lib/loop_mugiq.cpp:455-509) and Displace::doVectorDisplacement / swapAuxDispVec (lib/displace.cpp:47-67) around
+// those wrappers, with QUDA's field assignment and blas::zero restated as device memcpy / memset, so that the
+// reference's GPU path can be timed on the same B200 (it is NOT part of the product path).
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <gamma.h>
+#include <mugiq_contract_kernels.cuh>
+#include <mugiq_displace_kernels.cuh>
+#include <mugiq_util_kernels.cuh>
+
+// declarations of the reference's wrapper templates (include/loop_mugiq.h:280-311, include/displace.h:109-111; those
+// headers pull in QUDA's multigrid and MPI and are not needed here); the definitions and explicit instantiations come
+// from lib/contract_wrappers.cu
+template <typename Float> void copyGammaCoeffStructToSymbol();
+template <typename Float> void copyGammaMapStructToSymbol();
+template <typename Float>
+void createPhaseMatrixGPU(complex<Float> *phaseMatrix_d, const int *momMatrix_h, long long locV3, int Nmom, int FTSign,
+                          const int localL[], const int totalL[]);
+template <typename Float, QudaFieldOrder fieldOrder>
+void performLoopContraction(complex<Float> *loopData_d, ColorSpinorField *eVecL, ColorSpinorField *eVecR, Float sigma);
+template <typename Float>
+void convertIdxOrder_mapGamma(complex<Float> *dataPosMP_d, const complex<Float> *dataPos_d, int nData, int nLoop, int nParity,
+                              int volumeCB, const int localL[]);
+template <typename Float, QudaFieldOrder order>
+void performCovariantDisplacementVector(ColorSpinorField *dst, ColorSpinorField *src, cudaGaugeField *gauge,
+                                        DisplaceDir dispDir, DisplaceSign dispSign);
+
+namespace {
+
+// loopContract_kernel prints the first 11 sites of every call from the device (lib/mugiq_contract_kernels.cu:90-95):
+// keep the reference unmodified and send that to /dev/null
+struct Quiet {
+  int saved = -1;
+  explicit Quiet(bool on) {
+    if (!on) return;
+    fflush(stdout);
+    saved = dup(1);
+    const int nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1);
+    close(nul);
+  }
+  ~Quiet() {
+    if (saved < 0) return;
+    cudaDeviceSynchronize();
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+  }
+};
+
+int g_gamma_prec = 0;  // cGammaCoeff / cGammaMap hold the tables of one precision at a time (include/contract_util.cuh:16-17)
+void gamma_tables(int prec) {
+  if (g_gamma_prec == prec) return;
+  if (prec == 8) {
+    copyGammaCoeffStructToSymbol<double>();
+    copyGammaMapStructToSymbol<double>();
+  } else {
+    copyGammaCoeffStructToSymbol<float>();
+    copyGammaMapStructToSymbol<float>();
+  }
+  g_gamma_prec = prec;
+}
+
+template <typename Float>
+void contract_t(void *loop_d, void *vL, void *vR, double sigma, const int L[4], int order, QudaPrecision p) {
+  const QudaFieldOrder fo = order == 4 ? QUDA_FLOAT4_FIELD_ORDER : QUDA_FLOAT2_FIELD_ORDER;
+  ColorSpinorField l(vL, L, fo, p), r(vR, L, fo, p);
+  if (order == 4)
+    performLoopContraction<Float, QUDA_FLOAT4_FIELD_ORDER>((complex<Float> *)loop_d, &l, &r, (Float)sigma);
+  else
+    performLoopContraction<Float, QUDA_FLOAT2_FIELD_ORDER>((complex<Float> *)loop_d, &l, &r, (Float)sigma);
+}
+
+template <typename Float>
+void displace_t(void *dst, void *src, void *gauge_d, int dir, int sign, const int L[4], int order, int extended, QudaPrecision p) {
+  const QudaFieldOrder fo = order == 4 ? QUDA_FLOAT4_FIELD_ORDER : QUDA_FLOAT2_FIELD_ORDER;
+  ColorSpinorField d(dst, L, fo, p), s(src, L, fo, p);
+  // the reference always hands the kernel the extended gauge field (lib/displace.cpp:16-19,104-134), border 0 when no
+  // dimension is partitioned; extended == 0 exercises the kernel's other branch (getNbrLink)
+  cudaGaugeField g(gauge_d, L, extended ? QUDA_GHOST_EXCHANGE_EXTENDED : QUDA_GHOST_EXCHANGE_PAD);
+  if (order == 4)
+    performCovariantDisplacementVector<Float, QUDA_FLOAT4_FIELD_ORDER>(&d, &s, &g, (DisplaceDir)dir, (DisplaceSign)sign);
+  else
+    performCovariantDisplacementVector<Float, QUDA_FLOAT2_FIELD_ORDER>(&d, &s, &g, (DisplaceDir)dir, (DisplaceSign)sign);
+}
+
+}  // namespace
+
+extern "C" {
+
+// loop_d[x_eo + V4*G] += ... : performLoopContraction (lib/contract_wrappers.cu:88-115); fields in QUDA FLOAT2 / FLOAT4 order
+int mugiq_ref_contract(void *loop_d, void *vL_d, void *vR_d, double sigma, const int L[4], int prec, int order, int quiet) {
+  gamma_tables(prec);
+  Quiet q(quiet != 0);
+  if (prec == 8)
+    contract_t<double>(loop_d, vL_d, vR_d, sigma, L, order, QUDA_DOUBLE_PRECISION);
+  else
+    contract_t<float>(loop_d, vL_d, vR_d, sigma, L, order, QUDA_SINGLE_PRECISION);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// performCovariantDisplacementVector (lib/contract_wrappers.cu:171-198); gauge_d: [dir][parity][x_cb][3][3]
+int mugiq_ref_displace(void *dst_d, void *src_d, void *gauge_d, int dir, int sign, const int L[4], int prec, int order,
+                       int extended) {
+  if (prec == 8)
+    displace_t<double>(dst_d, src_d, gauge_d, dir, sign, L, order, extended, QUDA_DOUBLE_PRECISION);
+  else
+    displace_t<float>(dst_d, src_d, gauge_d, dir, sign, L, order, extended, QUDA_SINGLE_PRECISION);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// convertIdxOrder_mapGamma (lib/contract_wrappers.cu:133-156)
+int mugiq_ref_reorder(void *out_d, const void *in_d, int nLoop, const int L[4], int prec) {
+  gamma_tables(prec);
+  const int volumeCB = L[0] * L[1] * L[2] * L[3] / 2;
+  if (prec == 8)
+    convertIdxOrder_mapGamma<double>((complex<double> *)out_d, (const complex<double> *)in_d, 16 * nLoop, nLoop, 2, volumeCB, L);
+  else
+    convertIdxOrder_mapGamma<float>((complex<float> *)out_d, (const complex<float> *)in_d, 16 * nLoop, nLoop, 2, volumeCB, L);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// createPhaseMatrixGPU (lib/contract_wrappers.cu:50-77)
+int mugiq_ref_phase(void *phase_d, const int *mom_h, int Nmom, int ftsign, const int L[4], const int totalL[4], int prec) {
+  const long long locV3 = (long long)L[0] * L[1] * L[2];
+  if (prec == 8)
+    createPhaseMatrixGPU<double>((complex<double> *)phase_d, mom_h, locV3, Nmom, ftsign, L, totalL);
+  else
+    createPhaseMatrixGPU<float>((complex<float> *)phase_d, mom_h, locV3, Nmom, ftsign, L, totalL);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// The loop nest of Loop_Mugiq::computeCoarseLoop (lib/loop_mugiq.cpp:455-509) in FP64 on fields in QUDA order.
+// entries: nentries x {dir, sign, start, stop}; work_d: 3 fields (fineEvecL, fineEvecR, auxDispVec) of V4*12 complex.
+int mugiq_ref_loop(void *dataPos_d, void *const *evec_d, const double *sigma, int nev, void *gauge_d, const int *entries,
+                   int nentries, const int L[4], int order, void *work_d) {
+  gamma_tables(8);
+  Quiet q(true);
+  const size_t V4 = (size_t)L[0] * L[1] * L[2] * L[3];
+  const size_t fbytes = V4 * 12 * sizeof(complex<double>);
+  const size_t perLoop = 16 * V4;  // nElemPosLocPerLoop
+  char *w = static_cast<char *>(work_d);
+  void *fineL = w, *fineR = w + fbytes, *aux = w + 2 * fbytes;
+  complex<double> *pos = static_cast<complex<double> *>(dataPos_d);
+  size_t loopOffset = 1;  // nLoopOffset: slot 0 is the ultra-local loop
+  for (int id = -1; id < nentries; id++) {
+    const int dir = id < 0 ? 0 : entries[4 * id], sign = id < 0 ? 0 : entries[4 * id + 1];
+    const int start = id < 0 ? 0 : entries[4 * id + 2], stop = id < 0 ? 0 : entries[4 * id + 3];
+    const size_t nL = id < 0 ? 1 : (size_t)(stop - start + 1);
+    const size_t bufOffset = id < 0 ? 0 : perLoop * loopOffset;
+    cudaMemset(pos + bufOffset, 0, sizeof(complex<double>) * perLoop * nL);
+    for (int n = 0; n < nev; n++) {
+      cudaMemcpy(fineL, evec_d[n], fbytes, cudaMemcpyDeviceToDevice);  // *fineEvecL = *(eigsolve->eVecs[n])
+      cudaMemcpy(fineR, fineL, fbytes, cudaMemcpyDeviceToDevice);      // *fineEvecR = *fineEvecL
+      if (id >= 0) {
+        int dispCount = 0;
+        for (int idisp = 1; idisp <= stop; idisp++) {
+          // Displace::doVectorDisplacement: blas::zero(aux); kernel; swapAuxDispVec = two field copies
+          cudaMemset(aux, 0, fbytes);
+          displace_t<double>(aux, fineR, gauge_d, dir, sign, L, order, 1, QUDA_DOUBLE_PRECISION);
+          cudaMemcpy(fineR, aux, fbytes, cudaMemcpyDeviceToDevice);
+          cudaMemcpy(aux, fineR, fbytes, cudaMemcpyDeviceToDevice);
+          if (idisp >= start && idisp <= stop) {
+            contract_t<double>(pos + bufOffset + perLoop * dispCount, fineL, fineR, sigma[n], L, order, QUDA_DOUBLE_PRECISION);
+            dispCount++;
+          }
+        }
+      } else {
+        contract_t<double>(pos, fineL, fineR, sigma[n], L, order, QUDA_DOUBLE_PRECISION);
+      }
+    }
+    if (id >= 0) loopOffset += nL;
+  }
+  cudaDeviceSynchronize();
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // extern "C"

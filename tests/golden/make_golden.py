@@ -1,7 +1,8 @@
 """Regenerates tests/golden/loop_4x4x4x8.npz: seeds + outputs of the 4^3x8 / 16-eigenvector configuration
 (BASELINE.json configs[0]) on which the C++ oracle and the independent numpy restatement agree to 1e-13.
 The reference has no golden vectors of its own and cannot be built here (QUDA absent), so this fixture pins
-the oracle against regressions, not against the reference's binaries ("parity unpinned")."""
+the oracle against regressions; the fixture that pins it to the reference's own kernels is ref_kernels_4x4x4x8.npz
+(make_ref_golden.py)."""
 import os
 import sys
 
