@@ -39,6 +39,10 @@ WORKLOADS = {
                                               entries="+x:1,4;-x:1,4;+y:1,4;-y:1,4;+z:1,4;-z:1,4;+t:1,4;-t:1,4", p2max=4),
     # BASELINE.json configs[3], per-GPU share (1000 eigenvectors over 8 GPUs), ultra-local only
     "32x32x32x64_nev125_ulocal": dict(L=(32, 32, 32, 64), nev=125, entries="", p2max=0),
+    # BASELINE.json configs[4], per-GPU time slab of the 48^3x96 lattice on 8 GPUs (use with --tsplit --gpus 8): 300 of the
+    # 2000 eigenvectors are resident (102 GB of extended slabs per GPU; the full set has to stream from the host)
+    "48x48x48x12_nev300_ulocal+1hop8": dict(L=(48, 48, 48, 12), nev=300, entries="+x:1;-x:1;+y:1;-y:1;+z:1;-z:1;+t:1;-t:1",
+                                           p2max=1),
     # small case for quick checks
     "8x8x8x16_nev16_ulocal+1hop8": dict(L=(8, 8, 8, 16), nev=16, entries="+x:1;-x:1;+y:1;-y:1;+z:1;-z:1;+t:1;-t:1", p2max=1),
 }
@@ -151,6 +155,42 @@ def cpu_sample_size(wl, target_s):
     return int(max(2, min(wl["nev"], 2 * target_s / dt2)))
 
 
+def reference_gpu_rate(wl, nev_sample):
+    """The reference's OWN CUDA kernels and wrappers (oracle/_ref/libmugiq_ref.so: lib/contract_wrappers.cu +
+    lib/mugiq_*_kernels.cu compiled unmodified against oracle/quda_shim) in the reference's loop order
+    (lib/loop_mugiq.cpp:455-509 restated in oracle/ref_driver.cu) on this GPU, `nev_sample` eigenvectors of the workload.
+    A reported baseline (what the reference's GPU path does on a B200), not the product path.  None if the library was
+    not built (it needs /root/reference at build time) or no GPU is visible."""
+    try:
+        import torch
+        from oracle import ref_kernels as ref
+        if not (ref.available() and torch.cuda.is_available()):
+            return None
+        from mugiq_b200.params import parse_disp_entries, which_displace
+        L = wl["L"]
+        entries = []
+        if wl["entries"]:
+            _, ds, a, b = parse_disp_entries(wl["entries"])
+            entries = [which_displace(s) + (x, y) for s, x, y in zip(ds, a, b)]
+        V4 = int(np.prod(L))
+        evq = [torch.randn(V4, 12, dtype=torch.complex128, device="cuda") for _ in range(nev_sample)]  # QUDA FLOAT2 order
+        gauge = torch.randn(4, V4, 3, 3, dtype=torch.complex128, device="cuda")
+        sig = [0.01 + 0.001 * i for i in range(nev_sample)]
+        ref.compute_loop(evq[:1], sig[:1], gauge, entries, L)  # warm-up: module load, constant tables
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref.compute_loop(evq, sig, gauge, entries, L)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": nev_sample * V4 * loop_count(entries) / dt, "unit": UNIT, "kind": "reference kernels on this GPU",
+                "seconds": dt,
+                "sample": f"{nev_sample} of {wl['nev']} eigenvectors, full lattice, all {loop_count(entries)} loops; "
+                          "lib/contract_wrappers.cu + lib/mugiq_*_kernels.cu unmodified (oracle/_ref), loop nest of "
+                          "lib/loop_mugiq.cpp:455-509 restated around them, device printf of the contraction kernel sent to /dev/null"}
+    except Exception as exc:  # a baseline must never take the bench down
+        return {"unavailable": repr(exc)[:200]}
+
+
 def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -179,7 +219,7 @@ def run_reference(args, wl, name):
             "config": {"workload": name, "L": list(wl["L"]), "nev": wl["nev"], "entries": wl["entries"], "nLoop": nloop},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "reference_gpu": reference_gpu_rate(wl, min(wl["nev"], 20))}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -223,7 +263,9 @@ def run_ours(args, wl, name):
             tmax = max([b for s, b in zip(ds, stop) if s[1] == "t"] + [0])
         Lg = (L[0], L[1], L[2], L[3] * world)
         ts = TSplit(Lg, rank, world, tmax)
-        U = synth.random_gauge(Lg, seed=11)
+        # this rank's extended slab of one global field, generated on the device slice by slice (slice-keyed seeds)
+        U = synth.random_gauge_slab_torch(Lg, [(ts.t0 - ts.H + i) % Lg[3] for i in range(ts.Tl + 2 * ts.H)], seed=11,
+                                          device=torch.device("cuda", local_rank))
     else:
         U = synth.random_gauge(L, seed=11)
     prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
@@ -280,6 +322,7 @@ def run_ours(args, wl, name):
 
     sampler = ClockSampler(physical_device_index(local_rank))
     ms_step = timed(step_resident, args.steps, args.warmup, sampler)
+    halo_sides = getattr(loop, "tsplit_halo_sides", 2)
     report = ops.prof_report()
     launches = sum(v["launches"] for v in report.values())
     value = world * units_per_rank / (ms_step * 1e-3)
@@ -346,6 +389,14 @@ def run_ours(args, wl, name):
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{nev_s} of {nev} eigenvectors, full lattice, all {nLoop} loops, {dt:.1f} s (oracle port, OpenMP)"}
 
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if e2e is not None:
+            del loop_h, ev_h
+        del ev_d, es
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu_rate(wl, min(nev, 20))
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -355,9 +406,11 @@ def run_ours(args, wl, name):
                            "l2": f"inputs larger than L2 ({nev * V4 * 192 / 1e9:.2f} GB of eigenvectors read per step)",
                            "evec_batch": args.evec_batch,
                            "partition": ("lattice-T split, global T = %d, halo %d slices, %.1f MB of halo per rank and step over "
-                                         "NVLink" % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector() / 1e6))
+                                         "NVLink (%d-sided eigenvector halo; interior-only compute)"
+                                         % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector(sides=halo_sides) / 1e6, halo_sides))
                            if ts is not None else ("eigenvector shards" if world > 1 else "single GPU")},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
+                "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "gpu_launches": launches,
+                "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

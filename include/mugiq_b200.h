@@ -182,6 +182,17 @@ int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan);
 int mugiq_b200_loop_plan_nloop(const mugiq_b200_loop_plan_t *plan);
 int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed, int *nderived, int *ngroups,
                               long long *wilson_bytes);
+/* Lattice-T split (BASELINE config 5): a rank runs the plan on its time slab EXTENDED by halo slices.
+ *   set_t_range : accumulate() computes dataPos only on the time-slices [t_begin, t_end) of the plan's lattice (the
+ *                 rank's interior) and merely reads the others; finalize() still spans the whole lattice.
+ *   t_halo      : what the plan reads across a slab boundary - eigenvector slices below the interior (directly
+ *                 computed minus-t loops), above it (plus-t loops), and loop-buffer slices below it (minus-t loops
+ *                 DERIVED from their plus partner: the caller fetches the partner's top slices from the rank below
+ *                 instead of computing them, once per run instead of once per eigenvector).
+ * Replaces the per-hop exchangeGhost of lib/contract_wrappers.cu:166-174 and the extended gauge field of
+ * lib/displace.cpp:104-134 for a partitioned t direction. */
+int mugiq_b200_loop_plan_set_t_range(mugiq_b200_loop_plan_t *plan, int t_begin, int t_end);
+int mugiq_b200_loop_plan_t_halo(const mugiq_b200_loop_plan_t *plan, int *evec_lower, int *evec_upper, int *loop_lower);
 int mugiq_b200_loop_plan_accumulate(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, const void *const *evec_d,
                                     const double *sigma_h, int nvec, int accumulate, void *stream);
 int mugiq_b200_loop_plan_finalize(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, int accumulate, void *stream);

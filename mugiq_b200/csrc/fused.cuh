@@ -47,10 +47,11 @@ struct FusedVecTable {
 
 // maximum number of displaced loops per group for this lattice / precision (warp and shared-memory budget)
 int fused_max_loops_per_group(const LatGeom &g, int precision);
-// Launches one group (0..kFusedMaxLoops displaced loops, plus the ultra-local loop if ul_off >= 0) over the whole
-// lattice for up to kFusedMaxVec eigenvectors.
+// Launches one group (0..kFusedMaxLoops displaced loops, plus the ultra-local loop if ul_off >= 0) for up to kFusedMaxVec
+// eigenvectors over the sites of the time-slices [t_begin, t_end) (rounded outwards to whole tiles; the whole lattice
+// for 0, Lt): a rank of a lattice-T split computes its interior only and merely READS the halo slices.
 int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,
-                       const LatGeom &g, int precision, cudaStream_t stream);
+                       const LatGeom &g, int precision, cudaStream_t stream, int t_begin = 0, int t_end = -1);
 
 // ---- gauge-only helpers (wilson.cu) ---------------------------------------------------------------------
 // Wout(x) = Win(x) * U_dir(x + shift*dir)       (extends a plus-direction Wilson line by one link)

@@ -121,6 +121,7 @@ template <typename F> struct FusedArgs {
   F *dataPos;
   long long ul_off;    // complex offset of the ultra-local loop's block in dataPos, < 0: not in this launch
   int accumulate;
+  int tt0;             // first tile in t of this launch (time-slice range of a lattice-T split; 0 = whole lattice)
 };
 
 constexpr int kSmemHeader = 2048;  // barriers + slot table
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   const int bid = blockIdx.x;
   const int y0 = (bid % tl.nTy) * tl.TY;
   const int z0 = ((bid / tl.nTy) % tl.nTz) * tl.TZ;
-  const int t0 = (bid / (tl.nTy * tl.nTz)) * tl.TT;
+  const int t0 = (bid / (tl.nTy * tl.nTz) + A.tt0) * tl.TT;
 
   if (threadIdx.x == 0) {
     build_slots(st, A.grp, tl, g, kSite, y0, z0, t0);
@@ -599,14 +600,13 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
   return -1;
 }
 
-template <typename F, int ND> static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, cudaStream_t stream) {
+template <typename F, int ND> static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           smem_limit_bytes()));
     attr_set = true;
   }
-  const int grid = args.tl.nTy * args.tl.nTz * args.tl.nTt;
   loop_fused_kernel<F, ND><<<grid, kFusedThreads, smem, stream>>>(args);
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
@@ -614,7 +614,7 @@ template <typename F, int ND> static int launch_fused_nd(const FusedArgs<F> &arg
 
 template <typename F>
 static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,
-                        const LatGeom &g, int precision, cudaStream_t stream) {
+                        const LatGeom &g, int precision, cudaStream_t stream, int t_begin, int t_end) {
   FusedArgs<F> args;
   args.g = g;
   args.grp = grp;
@@ -625,6 +625,11 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   if (!choose_tiling(args.tl, grp, g, precision, smem_limit_bytes()))
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
+  // time-slice range -> whole tiles in t
+  const int tt0 = t_begin / args.tl.TT, tt1 = (t_end + args.tl.TT - 1) / args.tl.TT;
+  args.tt0 = tt0;
+  const int grid = args.tl.nTy * args.tl.nTz * (tt1 - tt0);
+  const double frac = (double)(tt1 - tt0) / (double)args.tl.nTt;  // share of the lattice this launch computes
   const size_t smem =
       kSmemHeader + (size_t)args.tl.units * 32 * 16 * sizeof(F) + (size_t)args.tl.nstages * args.tl.stage_bytes;
   // algorithmic (compulsory) bytes: every eigenvector site once, every link once, the accumulators once
@@ -633,25 +638,28 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   // FP64 work per (eigvec, site): 336 DFMA + 24 DMUL per displaced loop (W v: 144, scale: 24, colour trace: 192) and
   // 96 DFMA for the Hermitian ultra-local matrix (+24 DMUL when it runs alone); FMA = 2 flop
   const double flop_site = grp.nloops * (336.0 * 2 + 24.0) + (ul_off >= 0 ? 96.0 * 2 + (grp.nloops == 0 ? 24.0 : 0.0) : 0.0);
-  ProfScope prof(K_LOOP_FUSED, stream, (double)g.volume * (vt.nvec * S + grp.nloops * U + nl * Acc * (accumulate ? 2 : 1)),
-                 (double)g.volume * vt.nvec * flop_site);
+  ProfScope prof(K_LOOP_FUSED, stream, frac * (double)g.volume * (vt.nvec * S + grp.nloops * U + nl * Acc * (accumulate ? 2 : 1)),
+                 frac * (double)g.volume * vt.nvec * flop_site);
   switch (grp.nloops) {
-    case 0: return launch_fused_nd<F, 0>(args, smem, stream);
-    case 1: return launch_fused_nd<F, 1>(args, smem, stream);
-    case 2: return launch_fused_nd<F, 2>(args, smem, stream);
-    case 3: return launch_fused_nd<F, 3>(args, smem, stream);
-    default: return launch_fused_nd<F, 4>(args, smem, stream);
+    case 0: return launch_fused_nd<F, 0>(args, smem, grid, stream);
+    case 1: return launch_fused_nd<F, 1>(args, smem, grid, stream);
+    case 2: return launch_fused_nd<F, 2>(args, smem, grid, stream);
+    case 3: return launch_fused_nd<F, 3>(args, smem, grid, stream);
+    default: return launch_fused_nd<F, 4>(args, smem, grid, stream);
   }
 }
 
 int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,
-                       const LatGeom &g, int precision, cudaStream_t stream) {
+                       const LatGeom &g, int precision, cudaStream_t stream, int t_begin, int t_end) {
+  if (t_end < 0) t_end = g.L[3];
+  if (t_begin < 0 || t_begin >= t_end || t_end > g.L[3])
+    return set_error(MUGIQ_B200_EINVAL, "loop_fused: bad time-slice range [%d, %d) on Lt = %d", t_begin, t_end, g.L[3]);
   if (grp.nloops < 0 || grp.nloops > kFusedMaxLoops || (grp.nloops == 0 && ul_off < 0) || vt.nvec < 1 ||
       vt.nvec > kFusedMaxVec)
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: bad group (%d loops, %d eigenvectors)", grp.nloops, vt.nvec);
   return precision == MUGIQ_B200_PREC_DOUBLE
-             ? launch_fused<double>(dataPos_d, grp, ul_off, vt, accumulate, g, precision, stream)
-             : launch_fused<float>(dataPos_d, grp, ul_off, vt, accumulate, g, precision, stream);
+             ? launch_fused<double>(dataPos_d, grp, ul_off, vt, accumulate, g, precision, stream, t_begin, t_end)
+             : launch_fused<float>(dataPos_d, grp, ul_off, vt, accumulate, g, precision, stream, t_begin, t_end);
 }
 
 }  // namespace mugiq_b200

@@ -35,6 +35,7 @@ struct LoopPlan {
   int precision;
   int nLoop;
   bool symmetric;
+  int t_begin = 0, t_end = -1;  // time-slices the fused kernels compute (-1: all): interior of a lattice-T split slab
   std::vector<Comp> comps;
   std::vector<Derive> derives;
   std::vector<int> zero_slots;  // slots no hop reaches (start < 1): stay zero, as in the reference
@@ -214,7 +215,7 @@ static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *cons
     for (size_t gi = 0; gi < pl.groups.size(); gi++) {
       // slot 0 (ultra-local) is accumulated by the first group
       int rc = fused_group_launch(dataPos_d, pl.groups[gi], gi == 0 ? 0 : -1, vt, accumulate || done > 0, pl.g,
-                                  pl.precision, stream);
+                                  pl.precision, stream, pl.t_begin, pl.t_end);
       if (rc) return rc;
     }
   }
@@ -329,6 +330,32 @@ int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed
   if (nderived) *nderived = (int)plan->pl.derives.size();
   if (ngroups) *ngroups = (int)plan->pl.groups.size();
   if (wilson_bytes) *wilson_bytes = (long long)(plan->pl.nW * plan->pl.link_field_bytes());
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_loop_plan_set_t_range(mugiq_b200_loop_plan_t *plan, int t_begin, int t_end) {
+  const char *who = "mugiq_b200_loop_plan_set_t_range";
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "%s: plan is NULL", who);
+  if (t_begin < 0 || t_begin >= t_end || t_end > plan->pl.g.L[3])
+    return set_error(MUGIQ_B200_EINVAL, "%s: bad range [%d, %d) on Lt = %d", who, t_begin, t_end, plan->pl.g.L[3]);
+  plan->pl.t_begin = t_begin;
+  plan->pl.t_end = t_end;
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_loop_plan_t_halo(const mugiq_b200_loop_plan_t *plan, int *evec_lower, int *evec_upper, int *loop_lower) {
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_loop_plan_t_halo: plan is NULL");
+  int lo = 0, up = 0, ll = 0;
+  for (const LoopPlan::Comp &c : plan->pl.comps) {
+    if (c.dir != MUGIQ_B200_DIR_T) continue;
+    if (c.sign == MUGIQ_B200_SIGN_PLUS) up = std::max(up, c.len);
+    if (c.sign == MUGIQ_B200_SIGN_MINUS) lo = std::max(lo, c.len);
+  }
+  for (const LoopPlan::Derive &d : plan->pl.derives)
+    if (d.kind == 1 && d.dir == MUGIQ_B200_DIR_T) ll = std::max(ll, d.len);
+  if (evec_lower) *evec_lower = lo;
+  if (evec_upper) *evec_upper = up;
+  if (loop_lower) *loop_lower = ll;
   return MUGIQ_B200_OK;
 }
 

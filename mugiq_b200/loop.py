@@ -58,8 +58,10 @@ class Displace:
     def __init__(self, loopParams: MugiqLoopParam, L, dtype=torch.complex128, device="cuda"):
         if loopParams.gauge is None:
             raise MugiqError("Displace: loopParams.gauge is not set")
-        g0 = np.asarray(loopParams.gauge[0])
-        want = np.complex128 if dtype == torch.complex128 else np.complex64
+        g0 = loopParams.gauge[0]
+        want = dtype if isinstance(g0, torch.Tensor) else (np.complex128 if dtype == torch.complex128 else np.complex64)
+        if not isinstance(g0, torch.Tensor):
+            g0 = np.asarray(g0)
         # lib/displace.cpp:84-87: gauge precision must equal the template precision
         if g0.dtype != want:
             raise MugiqError(f"createCudaGaugeField: Incompatible precision settings between Displace template "
@@ -75,7 +77,12 @@ class Displace:
         self.dispSign = None
 
     def upload_gauge(self, loopParams: MugiqLoopParam):
-        """createCudaGaugeField (lib/displace.cpp:70-100): H2D copy of the host QDP-order links."""
+        """createCudaGaugeField (lib/displace.cpp:70-100): H2D copy of the host QDP-order links.  Links that already
+        live on the device (four [V4, 3, 3] CUDA tensors, e.g. a time slab generated in place) are adopted."""
+        if isinstance(loopParams.gauge[0], torch.Tensor) and loopParams.gauge[0].is_cuda:
+            self.gaugeField = torch.stack([loopParams.gauge[mu] for mu in range(4)]).contiguous()
+            self.gaugeVersion += 1
+            return self.gaugeField
         if self.gaugeField is None:
             self.gaugeField = ops.gauge_upload(loopParams.gauge, self.L, device=self.device)
         else:
@@ -166,7 +173,11 @@ class Loop_Mugiq:
             if tsplit is not None:  # replicated global links -> this rank's extended slab
                 import copy
                 lp = copy.copy(loopParams_)
-                lp.gauge = [tsplit.global_slab(np.asarray(loopParams_.gauge[mu]), site_dim=0) for mu in range(4)]
+                if isinstance(loopParams_.gauge[0], torch.Tensor):  # this rank's extended slab, already on the device
+                    if loopParams_.gauge[0].shape[0] != Lattice(self.L_run).volume:
+                        raise MugiqError("Loop_Mugiq: device links given to a T split must be the rank's extended slab")
+                else:
+                    lp.gauge = [tsplit.global_slab(np.asarray(loopParams_.gauge[mu]), site_dim=0) for mu in range(4)]
                 self.displace = Displace(lp, self.L_run, dtype=self.dtype, device=self.device)
             else:
                 self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
@@ -243,15 +254,29 @@ class Loop_Mugiq:
         es, ts = self.eigsolve, self.tsplit
         nb = max(1, min(self.stream_batch, es.nEv))
         batches = [(b0, min(es.nEv, b0 + nb)) for b0 in range(0, es.nEv, nb)]
+        # only the interior is computed; the halos are read.  Plus-t loops read eigenvector slices above the interior,
+        # minus-t loops that are computed directly read below it; minus-t loops DERIVED from their plus partner need the
+        # partner's loop values below the interior instead, fetched once after the eigenvector sum.
+        plan.set_t_range(ts.H, ts.H + ts.Tl)
+        lo, up, ll = plan.t_halo()
+        self.tsplit_halo_sides = int(lo > 0) + int(up > 0)
+        ext_kw = dict(group=self.group, device=self.device, lower=lo > 0, upper=up > 0)
         # the halo exchange of batch i+1 is posted before the kernels of batch i are launched, so it overlaps them
-        pending = ts.begin_extend(es.eVecs[batches[0][0]:batches[0][1]], group=self.group, device=self.device)
+        pending = ts.begin_extend(es.eVecs[batches[0][0]:batches[0][1]], **ext_kw)
         for i, (b0, b1) in enumerate(batches):
             cur = pending
             if i + 1 < len(batches):
                 n0, n1 = batches[i + 1]
-                pending = ts.begin_extend(es.eVecs[n0:n1], group=self.group, device=self.device)
+                pending = ts.begin_extend(es.eVecs[n0:n1], **ext_kw)
             ext = ts.finish_extend(cur)
             plan.accumulate(self.dataPosExt_d, list(ext), es.eVals_sigma[b0:b1], accumulate=b0 > 0)
+        if ll > 0:
+            slots, iL = [], 1
+            for (d, sgn, a, b) in self.cPrm.entries():
+                if d == 3 and sgn == 1:
+                    slots += list(range(iL, iL + b - a + 1))
+                iL += b - a + 1
+            ts.exchange_loop_halo(self.dataPosExt_d, slots, group=self.group)
         plan.finalize(self.dataPosExt_d)
 
     def _finish_tsplit(self):

@@ -190,6 +190,16 @@ class LoopPlan:
         check(_lib.load().mugiq_b200_loop_plan_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(w)))
         return {"computed": a.value, "derived": b.value, "groups": c.value, "wilson_bytes": w.value}
 
+    def set_t_range(self, t_begin, t_end):
+        """accumulate() computes only the time-slices [t_begin, t_end) (interior of a lattice-T split slab)."""
+        check(_lib.load().mugiq_b200_loop_plan_set_t_range(self._h, int(t_begin), int(t_end)))
+
+    def t_halo(self):
+        """(eigenvector slices read below the interior, above it, loop-buffer slices read below it)."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(_lib.load().mugiq_b200_loop_plan_t_halo(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def accumulate(self, dataPos, evecs, sigma, accumulate=False):
         _dev(dataPos, *evecs)
         n = len(evecs)

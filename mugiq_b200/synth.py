@@ -54,6 +54,29 @@ def random_evecs_torch(L, nEv, seed=0, device="cuda", dtype=None):
     return out
 
 
+def random_gauge_slab_torch(L_global, t_slices, seed=0, device="cuda"):
+    """Random SU(3) links of the given GLOBAL time-slices, generated on the device one slice at a time from a
+    slice-keyed generator: every rank of a lattice-T split builds its own extended slab (interior + halo slices) of the
+    SAME global field without ever holding the whole field (6.1 GB at 48^3x96).  Returns four [V4_slab, 3, 3] complex128
+    tensors in even/odd order of the slab lattice (Lx, Ly, Lz, len(t_slices)); the first slice must have the parity of
+    its global t (even slab offsets), as in TSplit.  Rows 1, 2 by Gram-Schmidt, row 3 = conj(row1 x row2): det = 1."""
+    import torch
+    Lx, Ly, Lz, T = (int(x) for x in L_global)
+    V3h = Lx * Ly * Lz // 2
+    nt = len(t_slices)
+    out = torch.empty((4, 2, nt, V3h, 3, 3), dtype=torch.complex128, device=device)
+    gen = torch.Generator(device=device)
+    for i, t in enumerate(t_slices):
+        gen.manual_seed((SEED0 + 104729 * (seed + 1) + 31 * (int(t) % T)) & 0x7FFFFFFF)
+        a = torch.view_as_complex(torch.randn((4, 2, V3h, 2, 3, 2), generator=gen, device=device, dtype=torch.float64))
+        u1 = a[..., 0, :] / a[..., 0, :].norm(dim=-1, keepdim=True)
+        b = a[..., 1, :] - (u1.conj() * a[..., 1, :]).sum(-1, keepdim=True) * u1
+        u2 = b / b.norm(dim=-1, keepdim=True)
+        u3 = torch.linalg.cross(u1, u2).conj()
+        out[:, :, i] = torch.stack([u1, u2, u3], dim=-2)
+    return [out[mu].reshape(2 * nt * V3h, 3, 3) for mu in range(4)]
+
+
 def sigmas(nEv):
     return 0.01 + 0.001 * np.arange(nEv, dtype=np.float64)
 

@@ -77,16 +77,21 @@ class TSplit:
         shp[site_dim] = 2 * self.Tl * self.V3h
         return out.reshape(shp)
 
-    def begin_extend(self, vectors, group=None, device=None):
+    def begin_extend(self, vectors, group=None, device=None, lower=True, upper=True):
         """Starts the extension of a batch of eigenvectors (sequence of [V4_loc, 12] tensors in local even/odd order, or
         one [nb, V4_loc, 12] tensor): the interiors are written into the extended buffer and the halo send/recv pairs are
-        posted (asynchronously: they overlap whatever is launched before finish_extend).  Returns a handle."""
+        posted (asynchronously: they overlap whatever is launched before finish_extend).  `lower` / `upper`: which halos
+        the kernels will read (LoopPlan.t_halo(): plus-t loops read above the interior, directly computed minus-t loops
+        below it; a halo nobody reads is neither sent nor filled).  Every rank must pass the same flags.
+        Returns a handle."""
         import torch.distributed as dist
         nb = len(vectors)
         H, Tl = self.H, self.Tl
         v0 = vectors[0]
         device = device if device is not None else v0.device
         ncomp = 12
+        lower, upper = bool(lower) and H > 0, bool(upper) and H > 0
+        top = bot = None
         if v0.numel() == 2 * (Tl + 2 * H) * self.V3h * ncomp and v0.device == torch.device(device) and H > 0:
             # the caller already stores its slab in the extended layout (halo slices allocated, interior filled): only the
             # halos move, nothing is copied
@@ -94,26 +99,36 @@ class TSplit:
             batch = _as_batch(views)  # one strided view when the fields are slices of one allocation: 2 copies, not 2*nb
             h = {"ext": None, "views": views, "batch": batch, "reqs": [], "from_dn": None, "from_up": None}
             if batch is not None:
-                top, bot = batch[:, :, Tl:Tl + H].contiguous(), batch[:, :, H:2 * H].contiguous()
+                if lower:
+                    top = batch[:, :, Tl:Tl + H].contiguous()
+                if upper:
+                    bot = batch[:, :, H:2 * H].contiguous()
             else:
-                top = torch.stack([v[:, Tl:Tl + H] for v in views])
-                bot = torch.stack([v[:, H:2 * H] for v in views])
+                if lower:
+                    top = torch.stack([v[:, Tl:Tl + H] for v in views])
+                if upper:
+                    bot = torch.stack([v[:, H:2 * H] for v in views])
         else:
             ext = torch.empty((nb, 2, Tl + 2 * H, self.V3h, ncomp), dtype=v0.dtype, device=device)
             for k in range(nb):
                 ext[k, :, H:H + Tl].copy_(vectors[k].reshape(2, Tl, self.V3h, ncomp), non_blocking=True)
             h = {"ext": ext, "views": None, "reqs": [], "from_dn": None, "from_up": None}
-            if H > 0:
+            if lower:
                 top = ext[:, :, Tl:Tl + H].contiguous()  # owned slices Tl-H..Tl-1: the LOWER halo of the rank above
+            if upper:
                 bot = ext[:, :, H:2 * H].contiguous()    # owned slices 0..H-1: the UPPER halo of the rank below
-        if H > 0:
+        if lower or upper:
             if self.world == 1:
                 h["from_dn"], h["from_up"] = top, bot
             else:
                 up, dn = (self.rank + 1) % self.world, (self.rank - 1) % self.world
-                h["from_dn"], h["from_up"] = torch.empty_like(top), torch.empty_like(bot)
-                ops = [dist.P2POp(dist.isend, top, up, group), dist.P2POp(dist.isend, bot, dn, group),
-                       dist.P2POp(dist.irecv, h["from_dn"], dn, group), dist.P2POp(dist.irecv, h["from_up"], up, group)]
+                ops = []
+                if lower:
+                    h["from_dn"] = torch.empty_like(top)
+                    ops += [dist.P2POp(dist.isend, top, up, group), dist.P2POp(dist.irecv, h["from_dn"], dn, group)]
+                if upper:
+                    h["from_up"] = torch.empty_like(bot)
+                    ops += [dist.P2POp(dist.isend, bot, dn, group), dist.P2POp(dist.irecv, h["from_up"], up, group)]
                 h["reqs"] = dist.batch_isend_irecv(ops)
                 h["keep"] = (top, bot)  # the send buffers must outlive the transfers
         return h
@@ -126,27 +141,54 @@ class TSplit:
             req.wait()
         if h["views"] is not None:
             if h["batch"] is not None:
-                h["batch"][:, :, :H] = h["from_dn"]
-                h["batch"][:, :, H + Tl:] = h["from_up"]
+                if h["from_dn"] is not None:
+                    h["batch"][:, :, :H] = h["from_dn"]
+                if h["from_up"] is not None:
+                    h["batch"][:, :, H + Tl:] = h["from_up"]
             else:
                 for k, v in enumerate(h["views"]):
-                    v[:, :H] = h["from_dn"][k]
-                    v[:, H + Tl:] = h["from_up"][k]
+                    if h["from_dn"] is not None:
+                        v[:, :H] = h["from_dn"][k]
+                    if h["from_up"] is not None:
+                        v[:, H + Tl:] = h["from_up"][k]
             return [v.reshape(2 * (Tl + 2 * H) * self.V3h, -1) for v in h["views"]]
         ext = h["ext"]
-        if H > 0:
+        if h["from_dn"] is not None:
             ext[:, :, :H] = h["from_dn"]
+        if h["from_up"] is not None:
             ext[:, :, H + Tl:] = h["from_up"]
         return ext.reshape(ext.shape[0], 2 * (Tl + 2 * H) * self.V3h, -1)
+
+    def exchange_loop_halo(self, dataPosExt, slots, group=None):
+        """Fills the LOWER halo slices of the given loop slots of the extended position-space buffer
+        [nLoop, 16, V4_ext] with the top interior slices of the rank below (periodic).  A minus-t loop derived from its
+        plus-t partner reads the partner at x - k t: for the first k interior slices that is the neighbour's interior,
+        which the neighbour has computed anyway - one exchange of 16*H*V3 complex per loop and run instead of an
+        eigenvector halo (and its contraction) per eigenvector."""
+        import torch.distributed as dist
+        H, Tl = self.H, self.Tl
+        if H == 0 or len(slots) == 0:
+            return
+        v = dataPosExt.reshape(dataPosExt.shape[0], dataPosExt.shape[1], 2, Tl + 2 * H, self.V3h)
+        idx = torch.as_tensor(list(slots), device=dataPosExt.device)
+        send = v[idx][:, :, :, Tl:Tl + H].contiguous()
+        if self.world == 1:
+            recv = send
+        else:
+            up, dn = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+            recv = torch.empty_like(send)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, recv, dn, group)]):
+                req.wait()
+        v[idx, :, :, :H] = recv
 
     def extend(self, interior, group=None):
         """[nb, V4_loc, 12] eigenvectors (local even/odd order) -> [nb, V4_ext, 12] with the halos of both neighbours.
         world == 1: the halos are the rank's own far slices (plain periodic lattice)."""
         return self.finish_extend(self.begin_extend(interior, group=group))
 
-    def halo_bytes_per_vector(self, itemsize=16):
-        """bytes one eigenvector sends (= receives) per extension: 2 neighbours x H slices x V3 sites x 12 complex"""
-        return 2 * self.H * 2 * self.V3h * 12 * itemsize
+    def halo_bytes_per_vector(self, itemsize=16, sides=2):
+        """bytes one eigenvector sends (= receives) per extension: `sides` neighbours x H slices x V3 sites x 12 complex"""
+        return sides * self.H * 2 * self.V3h * 12 * itemsize
 
     def gather_time(self, local_mom, group=None):
         """[Nmom, nData, Tl] per rank -> [Nmom, nData, T] on every rank (COMM_TIME gather + broadcast of the reference)."""

@@ -66,6 +66,21 @@ def test_single_rank_extension_is_the_periodic_wrap():
     assert all(o.data_ptr() == s.data_ptr() for o, s in zip(out, stored)) and torch.equal(torch.stack(out), want)
 
 
+def test_slab_gauge_generator_is_one_global_su3_field():
+    """Slice-keyed generator: unitary, det = 1, and two slabs agree wherever they hold the same global time-slice."""
+    Lg = (4, 4, 2, 8)
+    a = synth.random_gauge_slab_torch(Lg, [6, 7, 0, 1, 2, 3], seed=3, device="cpu")   # rank 0 of 4 ranks... with halo 2
+    b = synth.random_gauge_slab_torch(Lg, [0, 1, 2, 3, 4, 5], seed=3, device="cpu")
+    V3h = 4 * 4 * 2 // 2
+    for mu in range(4):
+        A = a[mu].reshape(2, 6, V3h, 3, 3)
+        B = b[mu].reshape(2, 6, V3h, 3, 3)
+        assert torch.equal(A[:, 2:6], B[:, 0:4])
+        eye = torch.eye(3, dtype=torch.complex128)
+        assert (A @ A.conj().transpose(-1, -2) - eye).abs().max() < 1e-13
+        assert (torch.linalg.det(A) - 1).abs().max() < 1e-13
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -86,6 +101,21 @@ def _worker(rank, world, port, out_dir):
     gathered = ts.gather_time(mom, group=dist.group.WORLD)
     want = torch.cat([torch.full((2, 3, ts.Tl), float(r), dtype=torch.complex128) + torch.arange(ts.Tl) for r in range(world)], -1)
     ok = ok and torch.equal(gathered, want)
+    # one-sided extension: only the requested halo is filled
+    up_only = ts.finish_extend(ts.begin_extend(inner, group=dist.group.WORLD, lower=False, upper=True))
+    full = ts.global_slab(g, site_dim=1).reshape(-1, 2, ts.Tl + 2 * ts.H, ts.V3h, 12)
+    got = up_only.reshape(full.shape)
+    ok = ok and torch.equal(got[:, :, ts.H:], full[:, :, ts.H:])
+    # loop-buffer halo: the lower halo slices of the chosen slots become the top interior slices of the rank below
+    rng = np.random.default_rng(7)
+    V4g = int(np.prod(L))
+    pos_g = torch.from_numpy(rng.standard_normal((4, 16, V4g)) + 1j * rng.standard_normal((4, 16, V4g)))
+    pos_ext = ts.global_slab(pos_g, site_dim=2).clone()
+    pv = pos_ext.reshape(4, 16, 2, ts.Tl + 2 * ts.H, ts.V3h)
+    pv[:, :, :, :ts.H] = 0
+    ts.exchange_loop_halo(pos_ext, [1, 3], group=dist.group.WORLD)
+    want_ext = ts.global_slab(pos_g, site_dim=2).reshape(pv.shape)
+    ok = ok and torch.equal(pv[[1, 3]][:, :, :, :ts.H], want_ext[[1, 3]][:, :, :, :ts.H]) and bool((pv[[0, 2]][:, :, :, :ts.H] == 0).all())
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
     dist.destroy_process_group()
 
@@ -97,11 +127,46 @@ def test_halo_exchange_gloo(tmp_path, world):
 
 
 @pytest.mark.gpu
+def test_tsplit_with_device_slab_links(oracle, monkeypatch):
+    """A rank may hand Loop_Mugiq its extended slab of links already on the device (bench.py does, for lattices whose
+    global field is too large to replicate on the host): same loops as from the replicated host field."""
+    from mugiq_b200.loop import Loop_Mugiq, Eigsolve
+    from mugiq_b200.params import MugiqLoopParam
+    Lg, world, nEv = (4, 4, 2, 8), 2, 3
+    Ug = synth.random_gauge_slab_torch(Lg, list(range(Lg[3])), seed=9, device="cuda")
+    U = np.stack([u.cpu().numpy() for u in Ug])
+    ev = synth.random_evecs_np(Lg, nEv, seed=62)
+    sig = synth.sigmas(nEv)
+    entries = [(3, 1, 1, 2), (2, 0, 1, 1)]   # no derived minus-t loop: no loop-buffer halo in this test
+    ref = oracle.compute_loop(ev, sig, U, entries, Lg)
+    evg = torch.from_numpy(ev).cuda()
+    parts = []
+    for rank in range(world):
+        ts = TSplit(Lg, rank, world, max_t_disp=2)
+        slab = synth.random_gauge_slab_torch(Lg, [(ts.t0 - ts.H + i) % Lg[3] for i in range(ts.Tl + 2 * ts.H)], seed=9, device="cuda")
+        monkeypatch.setattr(ts, "begin_extend", lambda vecs, group=None, device=None, lower=True, upper=True: len(vecs))
+        monkeypatch.setattr(ts, "finish_extend", lambda n, ts=ts: ts.global_slab(evg[:n], site_dim=1))
+        prm = MugiqLoopParam(gauge=slab)
+        prm.set_displacements("+t:1,2;-z:1")
+        prm.doMomProj = False
+        inner = _interior_of_global(ts, evg, 1).contiguous()
+        loop = Loop_Mugiq(prm, Eigsolve(list(inner), sig, ts.L_loc), tsplit=ts, stream_batch=nEv, group=object())
+        loop.computeCoarseLoop()
+        parts.append(loop.dataPos.numpy().reshape(ref.shape[0], 16, 2, ts.Tl, ts.V3h))
+    assert rel_err(np.concatenate(parts, axis=3).reshape(ref.shape), ref) < TOL_F64
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_tsplit_loop_matches_global_oracle(oracle, world, monkeypatch):
-    """Each (virtual) rank computes its time-slab with the fused kernels on the extended lattice; the stitched
-    position-space buffer and the gathered momentum-space buffer equal the oracle's on the global lattice.  The halos
-    are cut from the global field here (one process); the NCCL/gloo exchange itself is covered above."""
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_tsplit_loop_matches_global_oracle(oracle, world, symmetric, monkeypatch):
+    """Each (virtual) rank computes the INTERIOR of its time-slab with the fused kernels on the extended lattice; the
+    stitched position-space buffer and the gathered momentum-space buffer equal the oracle's on the global lattice.
+    The eigenvector halos are cut from the global field here (one process) and the loop-buffer halo of the derived
+    minus-t loops is passed between the virtual ranks by hand; the NCCL/gloo exchanges themselves are covered above.
+    symmetric=False (MUGIQ_B200_NO_PM_SYMMETRY=1): every loop is computed directly, both eigenvector halos are read."""
+    if not symmetric:
+        monkeypatch.setenv("MUGIQ_B200_NO_PM_SYMMETRY", "1")
     from mugiq_b200.loop import Loop_Mugiq, Eigsolve
     from mugiq_b200.params import MugiqLoopParam, momenta_up_to
     from oracle import numpy_check as npc
@@ -116,19 +181,53 @@ def test_tsplit_loop_matches_global_oracle(oracle, world, monkeypatch):
     ref = oracle.compute_loop(ev, sig, U, entries, Lg)
     ref_mom = npc.momentum_projection(ref, mom, -1, Lg)
     evg = torch.from_numpy(ev).cuda()
-    pos_parts, mom_parts = [], []
-    for rank in range(world):
+    H = 2
+    sent = {}  # rank -> the loop-buffer slices it sends upwards (recorded in pass 0, delivered in pass 1)
+
+    def run(rank, deliver):
         ts = TSplit(Lg, rank, world, max_t_disp=2)
-        monkeypatch.setattr(ts, "begin_extend", lambda vecs, group=None, device=None, ts=ts: len(vecs))
-        monkeypatch.setattr(ts, "finish_extend", lambda n, ts=ts: ts.global_slab(evg[:n], site_dim=1))
+
+        def begin(vecs, group=None, device=None, lower=True, upper=True):
+            return len(vecs), lower, upper
+
+        def finish(h):
+            n, lower, upper = h
+            ext = ts.global_slab(evg[:n], site_dim=1).clone()
+            v = ext.reshape(n, 2, ts.Tl + 2 * H, ts.V3h, 12)
+            if not lower:
+                v[:, :, :H] = float("nan")  # a halo the plan said it does not read must not influence the result
+            if not upper:
+                v[:, :, H + ts.Tl:] = float("nan")
+            return ext
+
+        def loop_halo(dataPosExt, slots, group=None):
+            v = dataPosExt.reshape(dataPosExt.shape[0], 16, 2, ts.Tl + 2 * H, ts.V3h)
+            idx = torch.as_tensor(list(slots), device=dataPosExt.device)
+            sent[rank] = v[idx][:, :, :, ts.Tl:ts.Tl + H].clone()
+            if deliver:
+                v[idx, :, :, :H] = sent[(rank - 1) % world]
+
+        monkeypatch.setattr(ts, "begin_extend", begin)
+        monkeypatch.setattr(ts, "finish_extend", finish)
+        monkeypatch.setattr(ts, "exchange_loop_halo", loop_halo)
+        monkeypatch.setattr(ts, "gather_time", lambda m, group=None: m)
         prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
         prm.set_displacements(entries_str)
         prm.set_momenta(mom)
         inner = _interior_of_global(ts, evg, 1).contiguous()
         loop = Loop_Mugiq(prm, Eigsolve(list(inner), sig, ts.L_loc), tsplit=ts, stream_batch=nEv,
                           group=object() if world > 1 else None)
-        monkeypatch.setattr(ts, "gather_time", lambda m, group=None: m)
         loop.computeCoarseLoop()
+        return ts, loop
+
+    # pass 0 records what every rank would send (its plus-t loops do not depend on the loop halo), pass 1 delivers it
+    for rank in range(world):
+        run(rank, deliver=False)
+    pos_parts, mom_parts = [], []
+    for rank in range(world):
+        ts, loop = run(rank, deliver=True)
+        if symmetric:
+            assert loop.tsplit_halo_sides == 1  # every minus-t loop has its plus partner: eigenvector halos travel one way
         pos_parts.append(loop.dataPos.numpy().reshape(ref.shape[0], 16, 2, ts.Tl, ts.V3h))
         mom_parts.append(loop.dataMom.numpy())
     got = np.concatenate(pos_parts, axis=3).reshape(ref.shape)
