@@ -276,7 +276,23 @@ def run_ours(args, wl, name):
     sig = synth.sigmas(nev) + (0.0 if ts is not None else 0.2 * rank)
     if ts is not None:
         # the slab is stored in the extended layout (halo slices allocated, filled by the exchange every step)
-        ev_d = synth.random_evecs_torch(ts.L_ext, nev, seed=100 + rank, device=dev)
+        if args.halo == "nccl":
+            ev_d = synth.random_evecs_torch(ts.L_ext, nev, seed=100 + rank, device=dev)
+        else:
+            # NVLink peer mode: the slabs live in one IPC-shareable allocation the two time neighbours map; halos are
+            # written straight into the neighbours' slabs (copy engines or SM kernel)
+            V4e = int(np.prod(ts.L_ext))
+            peer_buf = ops.PeerBuffer(nev * V4e * 12 * 16, device=dev)
+            ev_d = synth.random_evecs_torch(ts.L_ext, nev, seed=100 + rank, device=dev,
+                                            out=peer_buf.tensor((nev, V4e, 12), torch.complex128))
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, peer_buf.handle)
+                up_ptr = ops.peer_open(handles[(rank + 1) % world], dev)
+                dn_ptr = up_ptr if world == 2 else ops.peer_open(handles[(rank - 1) % world], dev)
+            else:
+                up_ptr = dn_ptr = peer_buf.ptr
+            ts.attach_peers(ev_d, up_ptr, dn_ptr, mode=0 if args.halo == "dma" else 1, group=group)
         es = Eigsolve(list(ev_d), sig, L, ext_volume=int(np.prod(ts.L_ext)))
     else:
         ev_d = synth.random_evecs_torch(L, nev, seed=100 + rank, device=dev)      # [nev, V4, 12] resident in HBM
@@ -406,8 +422,9 @@ def run_ours(args, wl, name):
                            "l2": f"inputs larger than L2 ({nev * V4 * 192 / 1e9:.2f} GB of eigenvectors read per step)",
                            "evec_batch": args.evec_batch,
                            "partition": ("lattice-T split, global T = %d, halo %d slices, %.1f MB of halo per rank and step over "
-                                         "NVLink (%d-sided eigenvector halo; interior-only compute)"
-                                         % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector(sides=halo_sides) / 1e6, halo_sides))
+                                         "NVLink (%d-sided eigenvector halo, transport %s; interior-only compute)"
+                                         % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector(sides=halo_sides) / 1e6, halo_sides,
+                                            args.halo))
                            if ts is not None else ("eigenvector shards" if world > 1 else "single GPU")},
                 "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": sampler.summary()}
@@ -428,6 +445,9 @@ def main():
     ap.add_argument("--evec-batch", type=int, default=200)
     ap.add_argument("--tsplit", action="store_true", help="partition the lattice in T over the GPUs (halo exchange) instead of "
                                                           "sharding eigenvectors")
+    ap.add_argument("--halo", default="dma", choices=["dma", "kernel", "nccl"],
+                    help="--tsplit halo transport: direct NVLink writes into the neighbours' slabs by the copy engines (dma) or "
+                         "an SM push kernel (kernel), or NCCL send/recv through staging buffers (nccl)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -232,6 +232,23 @@ long long mugiq_b200_momproj_pos_workspace_bytes(const mugiq_b200_geom_t *geom, 
 int mugiq_b200_momproj_pos(void *mom_d, const void *dataPos_d, const void *phase_eo_d, int nLoop, int Nmom,
                            const mugiq_b200_geom_t *geom, void *workspace_d, void *stream);
 
+/* ---- lattice-T split: halo slices over NVLink peer memory ------------------------------------------------------ */
+/* Replaces, for a partitioned t direction, ColorSpinorField::exchangeGhost (lib/contract_wrappers.cu:166-174: one
+ * host-staged nFace = 1 halo per hop and eigenvector).  Every rank (one process per GPU) stores its eigenvector slabs
+ * in the extended layout [vector][parity][t = 0 .. Lt_ext)[V3/2][12 complex] in one allocation made by peer_alloc; the
+ * 64-byte handle travels to the two time neighbours (any transport: the Python front end sends it over its process group),
+ * which map the allocation with peer_open.  halo_push_t then writes nslices boundary time-slices of a whole batch of
+ * vectors straight into the neighbour's halo slices over NVLink: mode 0 = one strided 2-D copy on the copy engines
+ * (no SM, no staging buffer, no pack / unpack), mode 1 = SM kernel with 128-bit peer stores.  The call is asynchronous
+ * on `stream`; making the neighbour wait for the data (e.g. a one-element all-reduce on the same stream) is the
+ * caller's job.  site_bytes = 192 (FP64) or 96 (FP32). */
+int mugiq_b200_peer_alloc(void **ptr_d, long long bytes, void *handle64);
+int mugiq_b200_peer_open(void **ptr_d, const void *handle64);
+int mugiq_b200_peer_close(void *ptr_d);
+int mugiq_b200_peer_free(void *ptr_d);
+int mugiq_b200_halo_push_t(void *dst_slabs_d, const void *src_slabs_d, int first_vec, int nvec, int Lt_ext, long long V3h,
+                           int site_bytes, int src_t, int dst_t, int nslices, int mode, void *stream);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* Per-kernel launch counters (always on) and CUDA-event timers (while enabled) around every kernel launch
  * of the library, recorded on the stream the kernel is launched on.  The reference only brackets

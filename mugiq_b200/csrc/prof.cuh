@@ -19,6 +19,7 @@ enum KernelId {
   K_MOMPROJ,          // momproj_*_kernel
   K_SPLITK_REDUCE,    // splitk_reduce_kernel
   K_CONVERT,          // convert_spinor_kernel
+  K_HALO_PUSH,        // halo_push_kernel / copy-engine 2-D copy into a time neighbour's slabs (peer.cu)
   K_COUNT
 };
 

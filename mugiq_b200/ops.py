@@ -300,6 +300,54 @@ def momproj_pos(dataPos, phase_eo, nLoop, L, workspace=None):
     return out
 
 
+# ---- NVLink peer memory for the lattice-T split (mugiq_b200_peer_*, mugiq_b200_halo_push_t) -------------------------
+class PeerBuffer:
+    """One device allocation other processes can map (CUDA IPC): `handle` (64 bytes) goes to the peers, who call
+    peer_open(handle).  tensor() views the allocation as a torch tensor without copying."""
+
+    def __init__(self, nbytes, device=None):
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(_lib.load().mugiq_b200_peer_alloc(C.byref(p), self.nbytes, h))
+        self.ptr = p.value
+        self.handle = h.raw
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self, shape, dtype):
+        return torch.as_tensor(self, device=self.device).view(dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            with torch.cuda.device(self.device):
+                check(_lib.load().mugiq_b200_peer_free(C.c_void_p(self.ptr)))
+            self.ptr = None
+
+
+def peer_open(handle, device=None):
+    p = C.c_void_p()
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        check(_lib.load().mugiq_b200_peer_open(C.byref(p), C.c_char_p(handle)))
+    return p.value
+
+
+def peer_close(ptr, device=None):
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        check(_lib.load().mugiq_b200_peer_close(C.c_void_p(ptr)))
+
+
+def halo_push_t(dst_ptr, src_ptr, first_vec, nvec, Lt_ext, V3h, src_t, dst_t, nslices, mode=0, site_bytes=192):
+    """Time-slices [src_t, src_t+nslices) of every (vector, parity) block of a batch of extended slabs -> slices
+    [dst_t, ...) of the same vectors in another (peer-mapped or local) allocation, on the current stream."""
+    check(_lib.load().mugiq_b200_halo_push_t(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(first_vec), int(nvec), int(Lt_ext),
+                                             int(V3h), int(site_bytes), int(src_t), int(dst_t), int(nslices), int(mode), _stream()))
+
+
 # ---- instrumentation (mugiq_b200_prof_*) ---------------------------------------------------------------
 def prof_enable(on=True):
     check(_lib.load().mugiq_b200_prof_enable(int(bool(on))))

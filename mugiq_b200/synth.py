@@ -38,15 +38,16 @@ def random_evecs_np(L, nEv, seed=0, dtype=np.complex128):
     return np.ascontiguousarray(v.astype(dtype))
 
 
-def random_evecs_torch(L, nEv, seed=0, device="cuda", dtype=None):
-    """Same shape generated on the device (bench-sized sets: 200 x 16^3x32 FP64 is 5 GB)."""
+def random_evecs_torch(L, nEv, seed=0, device="cuda", dtype=None, out=None):
+    """Same shape generated on the device (bench-sized sets: 200 x 16^3x32 FP64 is 5 GB); `out`: fill this tensor."""
     import torch
     dtype = dtype or torch.complex128
     lat = Lattice(L)
     gen = torch.Generator(device=device)
     gen.manual_seed((SEED0 + 7919 * (seed + 1)) & 0x7FFFFFFF)
     real = torch.float64 if dtype == torch.complex128 else torch.float32
-    out = torch.empty((nEv, lat.volume, 12), dtype=dtype, device=device)
+    if out is None:
+        out = torch.empty((nEv, lat.volume, 12), dtype=dtype, device=device)
     for n in range(nEv):  # one field at a time keeps the temporary small
         v = torch.randn((lat.volume, 12, 2), generator=gen, device=device, dtype=real)
         v /= v.norm()

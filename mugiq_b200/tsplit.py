@@ -49,6 +49,46 @@ class TSplit:
         self.L_ext = (Lx, Ly, Lz, self.Tl + 2 * H)
         self.V3h = Lx * Ly * Lz // 2
         self.t0 = self.rank * self.Tl  # first global time-slice owned
+        self.peer = None               # set by attach_peers: halos travel as direct NVLink writes into the neighbours' slabs
+
+    # ---- NVLink peer mode ------------------------------------------------------------------------------------------------
+    def attach_peers(self, slabs, up_ptr, dn_ptr, mode=0, group=None):
+        """`slabs`: this rank's eigenvectors [nvec, V4_ext, 12] (complex128) in ONE allocation made by ops.PeerBuffer;
+        `up_ptr` / `dn_ptr`: the same allocation of rank+1 / rank-1 mapped into this process (ops.peer_open; the rank's
+        own pointer when world == 1).  From now on begin_extend on views of `slabs` writes the boundary slices of the batch
+        straight into the neighbours' halo slices (mode 0: copy engines, mode 1: SM push kernel) on a high-priority side
+        stream, followed by a one-element all-reduce that tells every rank its halos have landed."""
+        if slabs.dim() != 3 or slabs.shape[1] != 2 * (self.Tl + 2 * self.H) * self.V3h or not slabs.is_contiguous():
+            raise ValueError("attach_peers: slabs must be a contiguous [nvec, V4_ext, 12] tensor")
+        self.peer = {"slabs": slabs, "up": int(up_ptr), "dn": int(dn_ptr), "mode": int(mode), "group": group,
+                     "stream": torch.cuda.Stream(device=slabs.device, priority=-1),
+                     "flag": torch.zeros(1, dtype=torch.float32, device=slabs.device)}
+
+    def _begin_extend_peer(self, vectors, lower, upper):
+        from . import ops
+        import torch.distributed as dist
+        pr = self.peer
+        slabs = pr["slabs"]
+        vec_bytes = slabs.shape[1] * slabs.shape[2] * slabs.element_size()
+        first = (vectors[0].data_ptr() - slabs.data_ptr()) // vec_bytes
+        nb = len(vectors)
+        if (vectors[0].data_ptr() - slabs.data_ptr()) % vec_bytes or any(
+                v.data_ptr() != slabs.data_ptr() + (first + k) * vec_bytes for k, v in enumerate(vectors)):
+            raise ValueError("begin_extend (peer mode): the batch must be consecutive vectors of the attached slabs")
+        H, Tl, Lt_ext = self.H, self.Tl, self.Tl + 2 * self.H
+        site_bytes = 12 * slabs.element_size()
+        cur = torch.cuda.current_stream(slabs.device)
+        pr["stream"].wait_stream(cur)  # the interiors are final
+        with torch.cuda.stream(pr["stream"]):
+            if upper:  # my first H interior slices are the upper halo of the rank below
+                ops.halo_push_t(pr["dn"], slabs.data_ptr(), first, nb, Lt_ext, self.V3h, H, H + Tl, H, pr["mode"], site_bytes)
+            if lower:  # my last H interior slices are the lower halo of the rank above
+                ops.halo_push_t(pr["up"], slabs.data_ptr(), first, nb, Lt_ext, self.V3h, Tl, 0, H, pr["mode"], site_bytes)
+            if self.world > 1 and (lower or upper):
+                dist.all_reduce(pr["flag"], group=pr["group"])  # every rank's pushes precede its contribution
+            ev = torch.cuda.Event()
+            ev.record(pr["stream"])
+        return {"peer_event": ev, "views": [v.reshape(2 * Lt_ext * self.V3h, -1) for v in vectors]}
 
     # ---- views: a full-lattice even/odd array [..., V4, C...] as [..., parity, t, V3/2, C...] ---------------------------
     def _view(self, a, Lt, site_dim):
@@ -91,6 +131,8 @@ class TSplit:
         device = device if device is not None else v0.device
         ncomp = 12
         lower, upper = bool(lower) and H > 0, bool(upper) and H > 0
+        if self.peer is not None and v0.numel() == 2 * (Tl + 2 * H) * self.V3h * ncomp:
+            return self._begin_extend_peer(vectors, lower, upper)
         top = bot = None
         if v0.numel() == 2 * (Tl + 2 * H) * self.V3h * ncomp and v0.device == torch.device(device) and H > 0:
             # the caller already stores its slab in the extended layout (halo slices allocated, interior filled): only the
@@ -137,6 +179,9 @@ class TSplit:
         """Waits for the halos of a begin_extend handle and returns the extended batch ([nb, V4_ext, 12], or the list of
         the caller's own extended vectors when they were extended in place)."""
         H, Tl = self.H, self.Tl
+        if "peer_event" in h:  # the neighbours wrote the halos in place
+            torch.cuda.current_stream().wait_event(h["peer_event"])
+            return h["views"]
         for req in h["reqs"]:
             req.wait()
         if h["views"] is not None:

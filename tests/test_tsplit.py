@@ -127,6 +127,39 @@ def test_halo_exchange_gloo(tmp_path, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("sides", [(True, True), (False, True), (True, False)])
+def test_peer_halo_push_single_rank(mode, sides):
+    """NVLink peer mode with one rank: the 'neighbours' are the rank's own allocation, so the pushed halos must be the
+    periodic wrap - by the copy engines (mode 0) and by the SM push kernel (mode 1), for a batch in the middle of the
+    slab array, and only the requested sides are written."""
+    from mugiq_b200 import ops
+    lower, upper = sides
+    g = torch.from_numpy(_global_field(nb=5)).cuda()
+    ts = TSplit(L, 0, 1, max_t_disp=2)
+    want = ts.global_slab(g, site_dim=1)                       # [5, V4_ext, 12]
+    buf = ops.PeerBuffer(want.numel() * 16)
+    try:
+        slabs = buf.tensor(tuple(want.shape), torch.complex128)
+        slabs.copy_(want)
+        v = slabs.reshape(5, 2, ts.Tl + 2 * ts.H, ts.V3h, 12)
+        v[:, :, :ts.H] = 7.0
+        v[:, :, ts.H + ts.Tl:] = 7.0
+        ts.attach_peers(slabs, buf.ptr, buf.ptr, mode=mode)
+        out = ts.finish_extend(ts.begin_extend(list(slabs[1:4]), lower=lower, upper=upper))
+        torch.cuda.synchronize()
+        assert len(out) == 3 and out[0].data_ptr() == slabs[1].data_ptr()
+        w = want.reshape(v.shape)
+        assert torch.equal(v[1:4, :, ts.H:ts.H + ts.Tl], w[1:4, :, ts.H:ts.H + ts.Tl])
+        assert torch.equal(v[1:4, :, :ts.H], w[1:4, :, :ts.H]) if lower else bool((v[1:4, :, :ts.H] == 7.0).all())
+        assert torch.equal(v[1:4, :, ts.H + ts.Tl:], w[1:4, :, ts.H + ts.Tl:]) if upper else bool((v[1:4, :, ts.H + ts.Tl:] == 7.0).all())
+        assert bool((v[0, :, :ts.H] == 7.0).all()) and bool((v[4, :, ts.H + ts.Tl:] == 7.0).all())  # other vectors untouched
+    finally:
+        del slabs, v
+        buf.free()
+
+
+@pytest.mark.gpu
 def test_tsplit_with_device_slab_links(oracle, monkeypatch):
     """A rank may hand Loop_Mugiq its extended slab of links already on the device (bench.py does, for lattices whose
     global field is too large to replicate on the host): same loops as from the replicated host field."""
