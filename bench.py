@@ -245,6 +245,9 @@ def run_ours(args, wl, name):
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its version on stdout, which must carry exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
@@ -298,7 +301,7 @@ def run_ours(args, wl, name):
         ev_d = synth.random_evecs_torch(L, nev, seed=100 + rank, device=dev)      # [nev, V4, 12] resident in HBM
         es = Eigsolve(list(ev_d), sig, L)
     loop = Loop_Mugiq(prm, es, device=dev, group=group, evec_batch=args.evec_batch,
-                      copy_pos_to_host=False, tsplit=ts, stream_batch=100 if ts is not None else 16)
+                      copy_pos_to_host=False, tsplit=ts, stream_batch=args.tsplit_batch if ts is not None else 16)
     nLoop = loop.cPrm.nLoop
     units_per_rank = nev * V4 * nLoop
 
@@ -448,6 +451,8 @@ def main():
     ap.add_argument("--halo", default="dma", choices=["dma", "kernel", "nccl"],
                     help="--tsplit halo transport: direct NVLink writes into the neighbours' slabs by the copy engines (dma) or "
                          "an SM push kernel (kernel), or NCCL send/recv through staging buffers (nccl)")
+    ap.add_argument("--tsplit-batch", type=int, default=100, help="--tsplit: eigenvectors per halo push / kernel launch (the push "
+                                                                  "of batch i+1 overlaps the kernels of batch i)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -215,8 +215,14 @@ class TSplit:
         if H == 0 or len(slots) == 0:
             return
         v = dataPosExt.reshape(dataPosExt.shape[0], dataPosExt.shape[1], 2, Tl + 2 * H, self.V3h)
-        idx = torch.as_tensor(list(slots), device=dataPosExt.device)
-        send = v[idx][:, :, :, Tl:Tl + H].contiguous()
+        slots = sorted(int(x) for x in slots)
+        # runs of consecutive slots are plain slices (no index tensor, no host-device synchronisation)
+        runs, a = [], 0
+        for k in range(1, len(slots) + 1):
+            if k == len(slots) or slots[k] != slots[k - 1] + 1:
+                runs.append((slots[a], slots[k - 1] + 1))
+                a = k
+        send = torch.cat([v[a:b, :, :, Tl:Tl + H] for a, b in runs]).contiguous()
         if self.world == 1:
             recv = send
         else:
@@ -224,7 +230,10 @@ class TSplit:
             recv = torch.empty_like(send)
             for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, recv, dn, group)]):
                 req.wait()
-        v[idx, :, :, :H] = recv
+        o = 0
+        for a, b in runs:
+            v[a:b, :, :, :H] = recv[o:o + b - a]
+            o += b - a
 
     def extend(self, interior, group=None):
         """[nb, V4_loc, 12] eigenvectors (local even/odd order) -> [nb, V4_ext, 12] with the halos of both neighbours.
