@@ -1,8 +1,9 @@
 """Momentum-space loop output ('next' row).  The reference writes parallel HDF5
-(lib/loop_mugiq.cpp:530-656); no HDF5 library exists in this image, so the same dataset tree
-/mom_%+d_%+d_%+d/<disp tag>/<GammaName>/loop with shape [T][2] is stored in a NumPy .npz archive whose keys
-are the HDF5 paths (a one-line h5py converter is shown in INTEGRATION.md).  Tag strings are the
-reference's, without its group2_tag[10] truncation (disp_+z_10 no longer collides with disp_+z_1)."""
+(lib/loop_mugiq.cpp:530-656): dataset tree /mom_%+d_%+d_%+d/<disp tag>/<GammaName>/loop with shape [T][2].  No HDF5
+library exists in this image, so a file name ending in .h5 / .hdf5 is written as a real HDF5 file by the self-contained
+writer mugiq_b200/h5min.py (same tree, native double / float); any other name gets a NumPy .npz archive whose keys are
+the HDF5 paths.  Tag strings are the reference's, without its group2_tag[10] truncation (disp_+z_10 no longer
+collides with disp_+z_1)."""
 import numpy as np
 
 
@@ -17,7 +18,12 @@ def momentum_loop_datasets(loop):
 def write_momentum_loops(filename, loop):
     if not filename:
         raise ValueError("write_momentum_loops: empty filename (option --loop-mom-space-filename)")
-    np.savez(filename, **momentum_loop_datasets(loop))
+    data = momentum_loop_datasets(loop)
+    if str(filename).lower().endswith((".h5", ".hdf5")):
+        from . import h5min
+        h5min.write(filename, {"/" + k: v for k, v in data.items()})
+    else:
+        np.savez(filename, **data)
 
 
 def read_loops_file(path):

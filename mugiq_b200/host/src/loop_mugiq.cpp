@@ -13,6 +13,7 @@
 #include <fstream>
 
 #include "comm_mugiq.h"
+#include "h5min.hpp"
 #include "host_util.h"
 
 template <typename Float, QudaFieldOrder fieldOrder> struct Loop_Mugiq<Float, fieldOrder>::LoopComputeParam {
@@ -311,6 +312,33 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   std::vector<std::string> tags{"disp_0"};
   for (int id = 0; id < cPrm->nDispEntries; id++)
     for (int len = cPrm->dispStart[id]; len <= cPrm->dispStop[id]; len++) tags.push_back("disp_" + cPrm->dispString[id] + "_" + std::to_string(len));
+  // a name ending in .h5 / .hdf5: a real HDF5 file with the reference's tree, written by the self-contained h5min.hpp
+  auto endsWith = [&](const char *suf) {
+    const size_t n = strlen(suf);
+    return momSpaceFilename.size() >= n && momSpaceFilename.compare(momSpaceFilename.size() - n, n, suf) == 0;
+  };
+  if (endsWith(".h5") || endsWith(".hdf5")) {
+    h5min::File h5;
+    std::vector<Float> tmp((size_t)2 * totT);
+    for (int im = 0; im < cPrm->Nmom; im++) {
+      char momTag[64];
+      snprintf(momTag, sizeof(momTag), "mom_%+d_%+d_%+d", cPrm->momMatrix[MOM_MATRIX_IDX(0, im)], cPrm->momMatrix[MOM_MATRIX_IDX(1, im)],
+               cPrm->momMatrix[MOM_MATRIX_IDX(2, im)]);
+      for (int iL = 0; iL < cPrm->nLoop; iL++)
+        for (int ig = 0; ig < N_GAMMA_; ig++) {
+          const complex<Float> *src = dataMom_bcast + (size_t)totT * ig + (size_t)totT * N_GAMMA_ * iL + (size_t)totT * nData * im;
+          for (int t = 0; t < totT; t++) {
+            tmp[2 * t] = src[t].real();
+            tmp[2 * t + 1] = src[t].imag();
+          }
+          h5.addDataset("/" + std::string(momTag) + "/" + tags[iL] + "/" + GammaName()[ig] + "/loop", {(uint64_t)totT, 2}, (int)sizeof(Float),
+                        tmp.data(), tmp.size() * sizeof(Float));
+        }
+    }
+    if (!h5.write(momSpaceFilename)) errorQuda("%s: cannot open %s for writing", __func__, momSpaceFilename.c_str());
+    printfQuda("%s: Momentum-space loops written to %s (HDF5)\n", __func__, momSpaceFilename.c_str());
+    return;
+  }
   std::string index = std::string("MUGIQ-B200 LOOPS v1 dtype ") + (sizeof(Float) == 8 ? "f64" : "f32") + "\n";
   std::vector<Float> payload;
   payload.reserve((size_t)2 * nElemMomTot);

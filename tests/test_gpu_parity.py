@@ -382,6 +382,14 @@ def test_loop_mugiq_end_to_end(ops, oracle, tmp_path):
     key = "mom_+1_+0_+0/disp_-y_2/g5g4/loop"
     im = mom.index([1, 0, 0])
     assert np.allclose(z[key][:, 0] + 1j * z[key][:, 1], ref_mom[im, 7 + 16 * 3, :], rtol=0, atol=1e-12 * np.abs(ref_mom).max())
+    # the same tree as a real HDF5 file (self-contained writer): every dataset of writeLoopsHDF5_Mom, [T][2] doubles
+    from mugiq_b200 import h5min
+    prm.fname_mom_h5 = str(tmp_path / "loops.h5")
+    loop.momSpaceFilename = prm.fname_mom_h5
+    loop.writeLoopsHDF5()
+    h = h5min.read(prm.fname_mom_h5)
+    assert len(h) == len(mom) * loop.cPrm.nLoop * 16 and set(h) == {"/" + k for k in z.files}
+    assert all(h["/" + k].shape == (L[3], 2) and np.array_equal(h["/" + k], z[k]) for k in z.files)
 
 
 def test_displace_mirror_state_machine(ops, oracle):

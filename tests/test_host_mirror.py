@@ -112,6 +112,21 @@ def test_driver_matches_oracle(driver, oracle, tmp_path, order, prec):
     im = mom.index([0, 1, 0])
     got = loops["/mom_+0_+1_+0/disp_+z_3/" + GAMMA_NAMES[7] + "/loop"]
     assert np.abs(got - ref_mom[im, 7 + 16 * 3, :]).max() < tol * np.abs(ref_mom).max()
+    if order == "site":
+        # the same run with an .h5 file name: a real HDF5 file (h5min.hpp), byte-identical to what the Python writer
+        # (mugiq_b200/h5min.py) produces for the same datasets, and readable by the independent reader
+        from mugiq_b200 import h5min
+        r = run(driver, "--dim", *L, "--prec", prec, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file",
+                tmp_path / "sig.bin", "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string",
+                "+z:1,3;-x:2;-t:1;+t:1", "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--loop-ft-sign",
+                "minus", "--loop-write-mom-space", "yes", "--loop-mom-space-filename", tmp_path / "loops.h5")
+        assert r.returncode == 0, r.stderr
+        blob = (tmp_path / "loops.h5").read_bytes()
+        h = h5min.loads(blob)
+        rdt = np.float64 if prec == "double" else np.float32
+        assert set(h) == set(loops) and all(v.shape == (L[3], 2) and v.dtype == rdt for v in h.values())
+        assert all(np.array_equal(h[k][:, 0] + 1j * h[k][:, 1], loops[k]) for k in loops)
+        assert h5min.dumps(h) == blob
 
 
 @pytest.mark.gpu
