@@ -183,6 +183,7 @@ class Loop_Mugiq:
                 self.displace = Displace(loopParams_, self.L, dtype=self.dtype, device=self.device)
         self._plan = None
         self._plan_version = -1
+        self._prepared = {}
         self._mp_workspace = None
         if self.cPrm.doMomProj and self.fused_momproj:
             need = ops.momproj_pos_workspace_bytes(self.L, self.precision, self.cPrm.nLoop, self.cPrm.Nmom)
@@ -225,7 +226,14 @@ class Loop_Mugiq:
             if es.eVecs[0].is_cuda:
                 for b0 in range(0, es.nEv, self.evec_batch):
                     b1 = min(es.nEv, b0 + self.evec_batch)
-                    plan.accumulate(self.dataPos_d, es.eVecs[b0:b1], es.eVals_sigma[b0:b1], accumulate=b0 > 0)
+                    # resident eigenvectors: the argument tables of a batch are built once and reused while the batch
+                    # still consists of the same device buffers
+                    key = (b0, b1, es.eVecs[b0].data_ptr(), es.eVecs[b1 - 1].data_ptr())
+                    prep = self._prepared.get((b0, b1))
+                    if prep is None or prep[0] != key:
+                        prep = (key, plan.prepare(es.eVecs[b0:b1], es.eVals_sigma[b0:b1]))
+                        self._prepared[(b0, b1)] = prep
+                    plan.accumulate(self.dataPos_d, prep[1], accumulate=b0 > 0)
             else:
                 self._accumulate_from_host(plan)
             # slots derived after the eigenvector sum (minus-direction partners, repeated entries); linear, so

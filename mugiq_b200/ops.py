@@ -168,6 +168,14 @@ def loop_accumulate(dataPos, evecs, sigma, gauge, entries, L, accumulate=False, 
     return dataPos
 
 
+class PreparedBatch:
+    """Host-side argument tables of an eigenvector batch (LoopPlan.prepare)."""
+    __slots__ = ("ptrs", "sigma", "n", "keep")
+
+    def __init__(self, ptrs, sigma, n, keep):
+        self.ptrs, self.sigma, self.n, self.keep = ptrs, sigma, n, keep
+
+
 class LoopPlan:
     """mugiq_b200_loop_plan_*: owns the Wilson lines and the launch schedule for one (gauge field, entry list)."""
 
@@ -200,13 +208,20 @@ class LoopPlan:
         check(_lib.load().mugiq_b200_loop_plan_t_halo(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def accumulate(self, dataPos, evecs, sigma, accumulate=False):
-        _dev(dataPos, *evecs)
+    def prepare(self, evecs, sigma):
+        """Host-side argument tables of a batch (pointer array, sigma array): building them costs ~0.1 ms for 200
+        eigenvectors, which a caller that runs the same resident batch again can pay once."""
+        _dev(*evecs)
         n = len(evecs)
-        sig = (C.c_double * n)(*[float(s) for s in sigma])
+        return PreparedBatch(ptr_array([v.data_ptr() for v in evecs]), (C.c_double * n)(*[float(s) for s in sigma]), n,
+                             list(evecs))  # the tensors are kept alive with the table
+
+    def accumulate(self, dataPos, evecs, sigma=None, accumulate=False):
+        """evecs: a sequence of eigenvector tensors (with `sigma`), or what prepare() returned for them."""
+        prep = evecs if isinstance(evecs, PreparedBatch) else self.prepare(evecs, sigma)
+        _dev(dataPos)
         with torch.cuda.device(dataPos.device):
-            check(_lib.load().mugiq_b200_loop_plan_accumulate(self._h, dataPos.data_ptr(),
-                                                              ptr_array([v.data_ptr() for v in evecs]), sig, n,
+            check(_lib.load().mugiq_b200_loop_plan_accumulate(self._h, dataPos.data_ptr(), prep.ptrs, prep.sigma, prep.n,
                                                               int(bool(accumulate)), _stream()))
         return dataPos
 
