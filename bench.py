@@ -342,6 +342,10 @@ def run_ours(args, wl, name):
     sampler = ClockSampler(physical_device_index(local_rank))
     ms_step = timed(step_resident, args.steps, args.warmup, sampler)
     halo_sides = getattr(loop, "tsplit_halo_sides", 2)
+    if ts is not None and getattr(loop, "_trace_on", False):
+        torch.cuda.synchronize()
+        print(f"[rank {rank}] T-split phases of the last step (device ms, host ms): " +
+              "; ".join(f"{n} {g:.3f}/{h:.3f}" for n, g, h in loop.trace_report()), file=sys.stderr, flush=True)
     report = ops.prof_report()
     launches = sum(v["launches"] for v in report.values())
     value = world * units_per_rank / (ms_step * 1e-3)
@@ -432,6 +436,14 @@ def run_ours(args, wl, name):
                 "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
+    if ts is not None and ts.peer is not None:
+        # unmap the neighbours' slabs before anybody frees its own
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            for ptr in {up_ptr, dn_ptr}:
+                ops.peer_close(ptr, dev)
+            dist.barrier()
     if world > 1:
         dist.destroy_process_group()
     return 0

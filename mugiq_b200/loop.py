@@ -184,9 +184,13 @@ class Loop_Mugiq:
         self._plan = None
         self._plan_version = -1
         self._prepared = {}
+        import os
+        self._trace_on = os.environ.get("MUGIQ_B200_TSPLIT_TRACE", "") not in ("", "0")
+        self._trace = []
         self._mp_workspace = None
         if self.cPrm.doMomProj and self.fused_momproj:
-            need = ops.momproj_pos_workspace_bytes(self.L, self.precision, self.cPrm.nLoop, self.cPrm.Nmom)
+            need = max(ops.momproj_pos_workspace_bytes(LL, self.precision, self.cPrm.nLoop, self.cPrm.Nmom)
+                       for LL in {tuple(self.L), tuple(self.L_run)})
             self._mp_workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
 
     # -- lib/loop_mugiq.cpp:102-158 ---------------------------------------------------------------------
@@ -256,6 +260,22 @@ class Loop_Mugiq:
                 self.performMomentumProjection()
         return self
 
+    def _mark(self, name):
+        """MUGIQ_B200_TSPLIT_TRACE=1: CUDA-event + host time stamps at the phase boundaries of a T-split step."""
+        if not self._trace_on:
+            return
+        import time
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._trace.append((name, ev, time.perf_counter()))
+
+    def trace_report(self):
+        """[(phase, device ms since the previous mark, host ms since the previous mark)] of the last traced step."""
+        out = []
+        for (n0, e0, h0), (n1, e1, h1) in zip(self._trace[:-1], self._trace[1:]):
+            out.append((n1, e0.elapsed_time(e1), (h1 - h0) * 1e3))
+        return out
+
     def _accumulate_tsplit(self, plan):
         """T split: every eigenvector batch is extended by the neighbours' halo slices (NCCL P2P over NVLink), then
         the fused kernel runs on the extended slab."""
@@ -265,6 +285,8 @@ class Loop_Mugiq:
         # only the interior is computed; the halos are read.  Plus-t loops read eigenvector slices above the interior,
         # minus-t loops that are computed directly read below it; minus-t loops DERIVED from their plus partner need the
         # partner's loop values below the interior instead, fetched once after the eigenvector sum.
+        self._trace = []
+        self._mark("start")
         plan.set_t_range(ts.H, ts.H + ts.Tl)
         lo, up, ll = plan.t_halo()
         self.tsplit_halo_sides = int(lo > 0) + int(up > 0)
@@ -277,7 +299,17 @@ class Loop_Mugiq:
                 n0, n1 = batches[i + 1]
                 pending = ts.begin_extend(es.eVecs[n0:n1], **ext_kw)
             ext = ts.finish_extend(cur)
-            plan.accumulate(self.dataPosExt_d, list(ext), es.eVals_sigma[b0:b1], accumulate=b0 > 0)
+            self._mark(f"halo wait {i}")
+            if ts.peer is not None:  # the slabs are extended in place: same device buffers every time
+                key = (b0, b1, ext[0].data_ptr(), ext[-1].data_ptr())
+                prep = self._prepared.get((b0, b1))
+                if prep is None or prep[0] != key:
+                    prep = (key, plan.prepare(list(ext), es.eVals_sigma[b0:b1]))
+                    self._prepared[(b0, b1)] = prep
+                plan.accumulate(self.dataPosExt_d, prep[1], accumulate=b0 > 0)
+            else:
+                plan.accumulate(self.dataPosExt_d, list(ext), es.eVals_sigma[b0:b1], accumulate=b0 > 0)
+            self._mark(f"kernels {i}")
         if ll > 0:
             slots, iL = [], 1
             for (d, sgn, a, b) in self.cPrm.entries():
@@ -285,12 +317,21 @@ class Loop_Mugiq:
                     slots += list(range(iL, iL + b - a + 1))
                 iL += b - a + 1
             ts.exchange_loop_halo(self.dataPosExt_d, slots, group=self.group)
+            self._mark("loop halo")
         plan.finalize(self.dataPosExt_d)
+        self._mark("finalize")
 
     def _finish_tsplit(self):
         p, ts = self.cPrm, self.tsplit
         # every rank owns its time-slices: no reduction, only the interior of the extended buffer is kept
-        self.dataPos_d.copy_(ts.interior(self.dataPosExt_d, site_dim=2))
+        # the interior of the extended buffer is the rank's position-space result; when only momentum-space data are
+        # wanted (no host copy of dataPos) the projection reads the extended buffer in place and the halo time-slices of
+        # its small result are dropped instead (dataPos_interior() still materialises the interior on demand)
+        self._project_ext = p.doMomProj and self.fused_momproj and not self.copy_pos_to_host
+        self._pos_valid = not self._project_ext
+        if not self._project_ext:
+            self.dataPos_d.copy_(ts.interior(self.dataPosExt_d, site_dim=2))
+        self._mark("interior copy")
         self._reduce_mom = False
         if self.copy_pos_to_host:
             if self.dataPos is None:
@@ -299,7 +340,16 @@ class Loop_Mugiq:
             torch.cuda.current_stream().synchronize()
         if p.doMomProj:
             self.performMomentumProjection()
+            self._mark("projection + gather + D2H")
         return self
+
+    def dataPos_interior(self):
+        """Device position-space buffer of this rank's own time-slices (T split: cut out of the extended buffer when the
+        last run skipped that copy)."""
+        if self.tsplit is not None and not getattr(self, "_pos_valid", True):
+            self.dataPos_d.copy_(self.tsplit.interior(self.dataPosExt_d, site_dim=2))
+            self._pos_valid = True
+        return self.dataPos_d
 
     def _loop_plan(self):
         """The Wilson lines + launch schedule for (gauge field, entries): built once, rebuilt when the gauge field
@@ -354,7 +404,11 @@ class Loop_Mugiq:
         p = self.cPrm
         if p.nData != p.nLoop * 16:
             raise MugiqError("performMomentumProjection: This function assumes that nData = nLoop * NGamma")
-        if self.fused_momproj:
+        if self.fused_momproj and getattr(self, "_project_ext", False):
+            ts = self.tsplit  # H is even: a site has the same parity in the extended and in the local lattice
+            ext = ops.momproj_pos(self.dataPosExt_d, self.phaseMatrix_d, p.nLoop, self.L_run, workspace=self._mp_workspace)
+            self.dataMom_d = ext[:, :, ts.H:ts.H + ts.Tl].contiguous()
+        elif self.fused_momproj:
             self.dataMom_d = ops.momproj_pos(self.dataPos_d, self.phaseMatrix_d, p.nLoop, self.L, workspace=self._mp_workspace)
         else:
             ops.reorder_mapgamma(self.dataPosMP_d, self.dataPos_d, p.nData, p.nLoop, self.L)

@@ -72,9 +72,15 @@ class TSplit:
         vec_bytes = slabs.shape[1] * slabs.shape[2] * slabs.element_size()
         first = (vectors[0].data_ptr() - slabs.data_ptr()) // vec_bytes
         nb = len(vectors)
-        if (vectors[0].data_ptr() - slabs.data_ptr()) % vec_bytes or any(
-                v.data_ptr() != slabs.data_ptr() + (first + k) * vec_bytes for k, v in enumerate(vectors)):
-            raise ValueError("begin_extend (peer mode): the batch must be consecutive vectors of the attached slabs")
+        # consecutive vectors of the attached slabs (checked once per distinct batch; the views are cached with it)
+        key = (vectors[0].data_ptr(), vectors[-1].data_ptr(), nb)
+        cached = pr.setdefault("batches", {}).get(key)
+        if cached is None:
+            if (vectors[0].data_ptr() - slabs.data_ptr()) % vec_bytes or any(
+                    v.data_ptr() != slabs.data_ptr() + (first + k) * vec_bytes for k, v in enumerate(vectors)):
+                raise ValueError("begin_extend (peer mode): the batch must be consecutive vectors of the attached slabs")
+            cached = [v.reshape(slabs.shape[1], -1) for v in vectors]
+            pr["batches"][key] = cached
         H, Tl, Lt_ext = self.H, self.Tl, self.Tl + 2 * self.H
         site_bytes = 12 * slabs.element_size()
         cur = torch.cuda.current_stream(slabs.device)
@@ -88,7 +94,7 @@ class TSplit:
                 dist.all_reduce(pr["flag"], group=pr["group"])  # every rank's pushes precede its contribution
             ev = torch.cuda.Event()
             ev.record(pr["stream"])
-        return {"peer_event": ev, "views": [v.reshape(2 * Lt_ext * self.V3h, -1) for v in vectors]}
+        return {"peer_event": ev, "views": cached}
 
     # ---- views: a full-lattice even/odd array [..., V4, C...] as [..., parity, t, V3/2, C...] ---------------------------
     def _view(self, a, Lt, site_dim):

@@ -217,7 +217,7 @@ def test_tsplit_loop_matches_global_oracle(oracle, world, symmetric, monkeypatch
     H = 2
     sent = {}  # rank -> the loop-buffer slices it sends upwards (recorded in pass 0, delivered in pass 1)
 
-    def run(rank, deliver):
+    def run(rank, deliver, copy_pos_to_host=True):
         ts = TSplit(Lg, rank, world, max_t_disp=2)
 
         def begin(vecs, group=None, device=None, lower=True, upper=True):
@@ -249,13 +249,19 @@ def test_tsplit_loop_matches_global_oracle(oracle, world, symmetric, monkeypatch
         prm.set_momenta(mom)
         inner = _interior_of_global(ts, evg, 1).contiguous()
         loop = Loop_Mugiq(prm, Eigsolve(list(inner), sig, ts.L_loc), tsplit=ts, stream_batch=nEv,
-                          group=object() if world > 1 else None)
+                          group=object() if world > 1 else None, copy_pos_to_host=copy_pos_to_host)
         loop.computeCoarseLoop()
         return ts, loop
 
     # pass 0 records what every rank would send (its plus-t loops do not depend on the loop halo), pass 1 delivers it
     for rank in range(world):
         run(rank, deliver=False)
+    if symmetric and world == 2:
+        # momentum-space data only: the projection reads the extended buffer in place, dataPos is cut out on demand
+        ts, loop = run(1, deliver=True, copy_pos_to_host=False)
+        assert loop._project_ext and rel_err(loop.dataMom.numpy(), ref_mom[:, :, ts.Tl:]) < TOL_F64
+        pos = loop.dataPos_interior().cpu().numpy().reshape(ref.shape[0], 16, 2, ts.Tl, ts.V3h)
+        assert rel_err(pos, ref.reshape(ref.shape[0], 16, 2, Lg[3], ts.V3h)[:, :, :, ts.Tl:]) < TOL_F64
     pos_parts, mom_parts = [], []
     for rank in range(world):
         ts, loop = run(rank, deliver=True)
