@@ -76,11 +76,12 @@ def ingest_spinor(src, order, L):
     return dst
 
 
-def ingest_spinor_batch(srcs, order, L):
-    """QUDA-native fields -> one [n, V4, 12] site-major tensor, one launch."""
+def ingest_spinor_batch(srcs, order, L, out=None):
+    """QUDA-native fields -> one [n, V4, 12] site-major tensor (`out` if given), one launch."""
     _dev(*srcs)
     n = len(srcs)
-    dst = torch.empty((n, _volume(L), 12), dtype=srcs[0].dtype, device=srcs[0].device)
+    dst = out if out is not None else torch.empty((n, _volume(L), 12), dtype=srcs[0].dtype, device=srcs[0].device)
+    _dev(dst)
     geom = make_geom(L, _prec(srcs[0]))
     with torch.cuda.device(dst.device):
         check(_lib.load().mugiq_b200_ingest_spinor_batch(ptr_array([dst[i].data_ptr() for i in range(n)]),
