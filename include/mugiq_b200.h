@@ -148,6 +148,18 @@ int mugiq_b200_displace(void *dst_d, const void *src_d, const void *gauge_d, int
 int mugiq_b200_displace_batch(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir,
                               int sign, const mugiq_b200_geom_t *geom, void *stream);
 
+/* ---- stages 1 and 2 directly on QUDA-native fields ------------------------------------------------------------ */
+/* The same two operations on fields in QUDA's FLOAT2 / FLOAT4 orders (order = MUGIQ_B200_ORDER_FLOAT2 / _FLOAT4), which is
+ * how the reference's kernels see them through FieldOrderCB (lib/mugiq_contract_kernels.cu:82-83,
+ * lib/mugiq_displace_kernels.cu:85-113): no layout conversion and no scratch field for the reference-shaped single
+ * calls performLoopContraction / performCovariantDisplacementVector (lib/contract_wrappers.cu:88-115,171-198); source
+ * AND destination of the displacement are native-order fields.  vL_d / vR_d / dst_d / src_d are HOST arrays of nvec
+ * device pointers; vR_d == NULL means vR = vL; accumulate as in mugiq_b200_contract_batch. */
+int mugiq_b200_contract_native(void *loop_d, const void *const *vL_d, const void *const *vR_d, const double *sigma_h, int nvec,
+                               int order, int accumulate, const mugiq_b200_geom_t *geom, void *stream);
+int mugiq_b200_displace_native(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir, int sign,
+                               int order, const mugiq_b200_geom_t *geom, void *stream);
+
 /* ---- stages 1+2 fused: the eigenvector loop of Loop_Mugiq::computeCoarseLoop -------------------- */
 /* For every eigenvector n and every loop iL (0 = ultra-local, then the entries in order, lengths
  * start..stop):  dataPos[x_eo + V4*(G + 16*iL)] (+)= (1/sigma_n) v_n(x)^dag Gamma_G (D^k v_n)(x).

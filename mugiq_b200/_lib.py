@@ -58,6 +58,8 @@ SYMBOLS = {
     "mugiq_b200_loop_plan_destroy": (_i, [_vp]),
     "mugiq_b200_loop_plan_nloop": (_i, [_vp]),
     "mugiq_b200_loop_plan_info": (_i, [_vp, _pi, _pi, _pi, C.POINTER(_ll)]),
+    "mugiq_b200_contract_native": (_i, [_vp, _pvp, _pvp, _pd, _i, _i, _i, _pg, _vp]),
+    "mugiq_b200_displace_native": (_i, [_pvp, _pvp, _i, _vp, _i, _i, _i, _pg, _vp]),
     "mugiq_b200_peer_alloc": (_i, [C.POINTER(_vp), _ll, _vp]),
     "mugiq_b200_peer_open": (_i, [C.POINTER(_vp), _vp]),
     "mugiq_b200_peer_close": (_i, [_vp]),

@@ -248,6 +248,47 @@ int mugiq_b200_displace_batch(void *const *dst_d, const void *const *src_d, int 
   return displace_batch(dst_d, src_d, nvec, gauge_d, dir, sign, g, geom->precision, (cudaStream_t)stream);
 }
 
+static int check_native_order(int order, const char *who) {
+  if (order != MUGIQ_B200_ORDER_FLOAT2 && order != MUGIQ_B200_ORDER_FLOAT4)
+    return set_error(MUGIQ_B200_EINVAL, "%s: order = %d is not a QUDA native order (FLOAT2 = 2, FLOAT4 = 4)", who, order);
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_contract_native(void *loop_d, const void *const *vL_d, const void *const *vR_d, const double *sigma_h, int nvec,
+                               int order, int accumulate, const mugiq_b200_geom_t *geom, void *stream) {
+  const char *who = "mugiq_b200_contract_native";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  if ((rc = check_native_order(order, who))) return rc;
+  REQUIRE_PTR(loop_d, who);
+  REQUIRE_PTR(vL_d, who);
+  REQUIRE_PTR(sigma_h, who);
+  if (nvec < 1) return set_error(MUGIQ_B200_EINVAL, "%s: nvec = %d must be positive", who, nvec);
+  for (int i = 0; i < nvec; i++)
+    if (!vL_d[i] || (vR_d && !vR_d[i])) return set_error(MUGIQ_B200_EINVAL, "%s: field %d is NULL", who, i);
+  return contract_batch_native(loop_d, vL_d, vR_d, sigma_h, nvec, order, accumulate, make_geom(geom->L), geom->precision,
+                               (cudaStream_t)stream);
+}
+
+int mugiq_b200_displace_native(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir, int sign,
+                               int order, const mugiq_b200_geom_t *geom, void *stream) {
+  const char *who = "mugiq_b200_displace_native";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  if ((rc = check_native_order(order, who))) return rc;
+  REQUIRE_PTR(dst_d, who);
+  REQUIRE_PTR(src_d, who);
+  REQUIRE_PTR(gauge_d, who);
+  if ((rc = check_dir_sign(dir, sign, who))) return rc;
+  if (nvec < 1) return set_error(MUGIQ_B200_EINVAL, "%s: nvec = %d must be positive", who, nvec);
+  for (int i = 0; i < nvec; i++) {
+    if (!dst_d[i] || !src_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: field %d is NULL", who, i);
+    if (dst_d[i] == src_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: dst and src of field %d must differ", who, i);
+  }
+  return displace_batch_native(dst_d, src_d, nvec, gauge_d, dir, sign, order, make_geom(geom->L), geom->precision,
+                               (cudaStream_t)stream);
+}
+
 long long mugiq_b200_loop_workspace_bytes(const mugiq_b200_geom_t *geom, int nvec,
                                           const mugiq_b200_disp_entry_t *entries, int nentries) {
   const char *who = "mugiq_b200_loop_workspace_bytes";

@@ -35,6 +35,11 @@ int displace(void *dst_d, const void *src_d, const void *gauge_d, int dir, int s
              int precision, cudaStream_t stream);
 int displace_batch(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir, int sign,
                    const LatGeom &g, int precision, cudaStream_t stream);
+// stages 1 and 2 on fields in QUDA's native FLOAT2 / FLOAT4 orders (native_order.cu)
+int contract_batch_native(void *loop_d, const void *const *vL, const void *const *vR, const double *sigma, int nvec, int order,
+                          int accumulate, const LatGeom &g, int precision, cudaStream_t stream);
+int displace_batch_native(void *const *dst_d, const void *const *src_d, int nvec, const void *gauge_d, int dir, int sign,
+                          int order, const LatGeom &g, int precision, cudaStream_t stream);
 // stages 1+2 fused
 long long loop_workspace_bytes(const LatGeom &g, int precision, int nvec, const mugiq_b200_disp_entry_t *entries,
                                int nentries);

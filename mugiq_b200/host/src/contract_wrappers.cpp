@@ -59,8 +59,16 @@ void performLoopContraction(quda::complex<Float> *loopData_d, quda::ColorSpinorF
   if (eVecL->SiteSubset() != QUDA_FULL_SITE_SUBSET || eVecR->SiteSubset() != QUDA_FULL_SITE_SUBSET)
     errorQuda("%s: This function supports only Full Site Subset spinors!", __func__);
   const mugiq_b200_geom_t geom = make_geom(eVecL->X(), precision_of<Float>());
-  SiteView L(eVecL, geom), R(eVecR, geom);
-  MUGIQ_CHECK(mugiq_b200_contract(loopData_d, L.ptr, eVecL == eVecR ? L.ptr : R.ptr, (double)sigma, &geom, nullptr));
+  if (eVecL->FieldOrder() != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER && eVecL->FieldOrder() == eVecR->FieldOrder()) {
+    // QUDA-native FLOAT2 / FLOAT4 fields are contracted in place: no conversion, no scratch field
+    const void *l = eVecL->V(), *r = eVecR->V();
+    const double s = (double)sigma;
+    MUGIQ_CHECK(mugiq_b200_contract_native(loopData_d, &l, eVecL == eVecR ? nullptr : &r, &s, 1, abi_order(eVecL->FieldOrder()), 1,
+                                           &geom, nullptr));
+  } else {
+    SiteView L(eVecL, geom), R(eVecR, geom);
+    MUGIQ_CHECK(mugiq_b200_contract(loopData_d, L.ptr, eVecL == eVecR ? L.ptr : R.ptr, (double)sigma, &geom, nullptr));
+  }
   HOST_CUDA(cudaDeviceSynchronize());
 }
 
@@ -80,11 +88,19 @@ void performCovariantDisplacementVector(quda::ColorSpinorField *dst, quda::Color
                                         quda::cudaGaugeField *gauge, DisplaceDir dispDir, DisplaceSign dispSign) {
   if (dst->SiteSubset() != QUDA_FULL_SITE_SUBSET || src->SiteSubset() != QUDA_FULL_SITE_SUBSET)
     errorQuda("%s: This function supports only Full Site Subset spinors!", __func__);
-  if (dst->FieldOrder() != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER)
-    errorQuda("%s: the destination must be a site-major field", __func__);
   const mugiq_b200_geom_t geom = make_geom(src->X(), precision_of<Float>());
-  SiteView S(src, geom);
-  MUGIQ_CHECK(mugiq_b200_displace(dst->V(), S.ptr, gauge->Gauge_p(), (int)dispDir, (int)dispSign, &geom, nullptr));
+  if (src->FieldOrder() != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER && src->FieldOrder() == dst->FieldOrder()) {
+    // source and destination in the same QUDA-native order: displaced in place of the layout
+    void *d = dst->V();
+    const void *s = src->V();
+    MUGIQ_CHECK(mugiq_b200_displace_native(&d, &s, 1, gauge->Gauge_p(), (int)dispDir, (int)dispSign, abi_order(src->FieldOrder()),
+                                           &geom, nullptr));
+  } else {
+    if (dst->FieldOrder() != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER)
+      errorQuda("%s: a destination in a QUDA-native order needs a source in the same order", __func__);
+    SiteView S(src, geom);
+    MUGIQ_CHECK(mugiq_b200_displace(dst->V(), S.ptr, gauge->Gauge_p(), (int)dispDir, (int)dispSign, &geom, nullptr));
+  }
   HOST_CUDA(cudaDeviceSynchronize());
 }
 

@@ -146,6 +146,33 @@ def displace_batch(dsts, srcs, gauge, direction, sign, L):
     return dsts
 
 
+def contract_native(loop, vLs, vRs, sigma, order, L, accumulate=True):
+    """Contraction of fields in QUDA FLOAT2 (order 2) / FLOAT4 (order 4) order, no layout conversion."""
+    _dev(loop, *vLs)
+    if vRs is not None:
+        _dev(*vRs)
+    n = len(vLs)
+    sig = (C.c_double * n)(*[float(s) for s in sigma])
+    geom = make_geom(L, _prec(loop))
+    with torch.cuda.device(loop.device):
+        check(_lib.load().mugiq_b200_contract_native(
+            loop.data_ptr(), ptr_array([v.data_ptr() for v in vLs]),
+            ptr_array([v.data_ptr() for v in vRs]) if vRs is not None else None, sig, n, int(order), int(bool(accumulate)),
+            C.byref(geom), _stream()))
+    return loop
+
+
+def displace_native(dsts, srcs, gauge, direction, sign, order, L):
+    """One hop on fields in QUDA FLOAT2 / FLOAT4 order (source and destination)."""
+    _dev(gauge, *dsts, *srcs)
+    geom = make_geom(L, _prec(srcs[0]))
+    with torch.cuda.device(gauge.device):
+        check(_lib.load().mugiq_b200_displace_native(ptr_array([d.data_ptr() for d in dsts]),
+                                                     ptr_array([s.data_ptr() for s in srcs]), len(srcs), gauge.data_ptr(),
+                                                     int(direction), int(sign), int(order), C.byref(geom), _stream()))
+    return dsts
+
+
 def loop_workspace_bytes(L, precision, nvec, entries):
     geom = make_geom(L, precision)
     return check(_lib.load().mugiq_b200_loop_workspace_bytes(C.byref(geom), nvec, entry_array(entries), len(entries)))

@@ -83,6 +83,41 @@ def test_reference_displacement_kernel(ref, ops, oracle, L, order, extended):
             assert rel_err(host(mine), got) < 1e-14, (d, s)
 
 
+@pytest.mark.parametrize("L", [(4, 4, 4, 8), (8, 4, 2, 6), (6, 2, 4, 2)])
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("prec", [8, 4])
+def test_native_order_kernels_against_reference_kernels(ref, ops, oracle, L, order, prec):
+    """mugiq_b200_contract_native / _displace_native work on the very FLOAT2 / FLOAT4 buffers the reference's kernels read
+    through FieldOrderCB: same inputs in place, no layout conversion on either side."""
+    n = 4
+    ev = synth.random_evecs_np(L, 2 * n, seed=54).astype(cdt(prec))
+    U = synth.random_gauge(L, seed=54).astype(cdt(prec))
+    V4 = ev.shape[1]
+    tol = TOL_F64 if prec == 8 else TOL_F32
+    q = [ref.site_to_quda(dev(ev[i]), order) for i in range(2 * n)]
+    sig = [0.3 + 0.1 * i for i in range(n)]
+    loop_ref = torch.zeros((16, V4), dtype=q[0].dtype, device="cuda")
+    for i in range(n):
+        ref.contract(loop_ref, q[i], q[n + i], sig[i], L, order)
+    loop_new = torch.full_like(loop_ref, 2.0)
+    ops.contract_native(loop_new, q[:n], q[n:], sig, order, L, accumulate=False)
+    assert rel_err(host(loop_new), host(loop_ref)) < tol
+    ops.contract_native(loop_new, q[:1], None, sig[:1], order, L, accumulate=True)       # vR = vL, accumulating
+    ref.contract(loop_ref, q[0], q[0], sig[0], L, order)
+    assert rel_err(host(loop_new), host(loop_ref)) < tol
+    gd = dev(U)
+    for d in range(4):
+        for s in (0, 1):
+            outs_ref = [torch.zeros_like(q[0]) for _ in range(3)]
+            for i in range(3):
+                ref.displace(outs_ref[i], q[i], gd, d, s, L, order, True)
+            outs = [torch.full_like(q[0], 9.0) for _ in range(3)]
+            ops.displace_native(outs, q[:3], gd, d, s, order, L)
+            for i in range(3):
+                assert rel_err(host(outs[i]), host(outs_ref[i])) < (1e-14 if prec == 8 else 1e-6), (d, s, i)
+            assert rel_err(host(ref.quda_to_site(outs[0], order)), oracle.displace(ev[0], U, d, s, L)) < (1e-14 if prec == 8 else 1e-6)
+
+
 @pytest.mark.parametrize("L", [(4, 4, 4, 8), (8, 2, 6, 4), (6, 4, 2, 3)])
 @pytest.mark.parametrize("prec", [8, 4])
 def test_reference_reorder_kernel(ref, ops, oracle, L, prec):

@@ -99,6 +99,17 @@ def bench_lattice(L, nvec, out):
     for d, s in ((0, 1), (1, 0), (3, 1)):
         ms, b = timeit(lambda: ops.displace_batch(vr[:nb], vl[:nb], gauge, d, s, L), flush=not big)
         out.append(row(f"displace_batch x{nb} dir={d} sign={s}", L, ms, b, V4 * (nb * 2 * S + U)))
+    # the same two stages on fields in QUDA FLOAT2 order (thread = site, coalesced without staging)
+    ms, b = timeit(lambda: ops.contract_native(loop, vl, vr, sig, 2, L, accumulate=False), flush=not big)
+    out.append(row(f"contract_native FLOAT2 vL!=vR x{nvec}", L, ms, b, V4 * (nvec * 2 * S + A)))
+    ms, b = timeit(lambda: ops.contract_native(loop, vl[:1], vr[:1], sig[:1], 2, L, accumulate=True))
+    out.append(row("contract_native FLOAT2 single pair", L, ms, b, V4 * (2 * S + 2 * A)))
+    nbn = min(nvec, 16)
+    for d, s in ((0, 1), (3, 0)):
+        ms, b = timeit(lambda: ops.displace_native(vr[:nbn], vl[:nbn], gauge, d, s, 2, L), flush=not big)
+        out.append(row(f"displace_native FLOAT2 x{nbn} dir={d} sign={s}", L, ms, b, V4 * (nbn * 2 * S + U)))
+        ms, b = timeit(lambda: ops.displace_native(vr[:1], vl[:1], gauge, d, s, 2, L))
+        out.append(row(f"displace_native FLOAT2 single dir={d} sign={s}", L, ms, b, V4 * (2 * S + U)))
     del ev2, vr
 
     # a8 reorder
