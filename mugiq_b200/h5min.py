@@ -103,8 +103,9 @@ class _Writer:
         space = struct.pack("<BBB5x", 1, arr.ndim, 0) + b"".join(struct.pack("<Q", d) for d in arr.shape)
         fill = struct.pack("<BBBB", 2, 2, 2, 0)  # v2: allocate late, write fill if set, fill value undefined
         layout = struct.pack("<BBQQ", 3, 1, raw, arr.nbytes)
-        return self.alloc(_object_header([_message(0x0001, space, 1), _message(0x0003, _datatype_float(arr.itemsize), 1),
-                                          _message(0x0005, fill, 1), _message(0x0008, layout)]))
+        # message flags as the library sets them (bit 0 = constant): dataspace 0, datatype / fill value / layout 1
+        return self.alloc(_object_header([_message(0x0001, space, 0), _message(0x0003, _datatype_float(arr.itemsize), 1),
+                                          _message(0x0005, fill, 1), _message(0x0008, layout, 1)]))
 
     def group(self, node):
         """Writes the objects below `node`, then its heap, symbol-table node, B-tree and object header.
@@ -142,7 +143,7 @@ class _Writer:
             slots += struct.pack("<QQ", snod_addr, offs[-1])
         tree += slots + b"\0" * ((2 * INTERNAL_K + 1) * 8 + 2 * INTERNAL_K * 8 - len(slots))
         tree_addr = self.alloc(tree)
-        oh_addr = self.alloc(_object_header([_message(0x0011, struct.pack("<QQ", tree_addr, heap_addr))]))
+        oh_addr = self.alloc(_object_header([_message(0x0011, struct.pack("<QQ", tree_addr, heap_addr), 1)]))
         return oh_addr, tree_addr, heap_addr
 
     def finish(self, root):

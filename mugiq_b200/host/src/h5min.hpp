@@ -100,7 +100,7 @@ class File {
     put<uint8_t>(layout, 1);
     put<uint64_t>(layout, raw);
     put<uint64_t>(layout, (uint64_t)d.raw.size());
-    return alloc(objectHeader({message(0x0001, space, 1), message(0x0003, type, 1), message(0x0005, fill, 1), message(0x0008, layout, 0)}));
+    return alloc(objectHeader({message(0x0001, space, 0), message(0x0003, type, 1), message(0x0005, fill, 1), message(0x0008, layout, 1)}));
   }
   struct GroupAddr {
     uint64_t oh, tree, heap;
@@ -170,7 +170,7 @@ class File {
     std::vector<char> st;
     put<uint64_t>(st, treeAddr);
     put<uint64_t>(st, heapAddr);
-    return {alloc(objectHeader({message(0x0011, st, 0)})), treeAddr, heapAddr};
+    return {alloc(objectHeader({message(0x0011, st, 1)})), treeAddr, heapAddr};
   }
   static size_t maxEntries(const Node &n) {
     size_t m = n.entries();

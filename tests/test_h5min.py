@@ -51,6 +51,19 @@ def test_writer_uses_the_encodings_of_the_library():
     assert real.at(ta, 8) == mine.at(tb, 8) and real.at(ta + 24, 8) == mine.at(tb + 24, 8)  # B-tree node header, first key
     assert real.at(ha, 8) == mine.at(hb, 8)                                             # local heap signature + version
     assert real.internal_k == mine.internal_k == 16 and real.leaf_k == mine.leaf_k == 4
+    # message flags (bit 0 = constant) of the messages both files have
+    def flags(r, oh):
+        out, pos = {}, oh + 16
+        for _ in range(struct.unpack("<H", r.at(oh + 2, 2))[0]):
+            t, sz, fl = struct.unpack("<HHB", r.at(pos, 5))
+            out[t] = fl
+            pos += 8 + sz
+        return out
+    (_, oh_a), = real.links(ta, ha)
+    (_, oh_b), = mine.links(tb, hb)
+    fa, fb = flags(real, oh_a), flags(mine, oh_b)
+    assert all(fa[t] == fb[t] for t in (0x0001, 0x0003, 0x0005, 0x0008))
+    assert flags(real, real.root_oh)[0x0011] == flags(mine, mine.root_oh)[0x0011]
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
