@@ -380,6 +380,14 @@ def run_ours(args, wl, name):
                     "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                                     "GBps": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
                                 for k, v in report.items()}}
+        # stage 4 (momentum projection) separately, as SURVEY 8d asks: useful FP64 TFLOP/s (8*M*N*K) against the measured
+        # DMMA peak; with few momenta (N <~ 12) the projection is HBM bound and the GB/s figure above is the relevant one
+        mp = report.get("momproj")
+        if mp and mp["ms"] > 0 and mp.get("alg_flops", 0) > 0:
+            tf = mp["alg_flops"] / (mp["ms"] * 1e-3) / 1e12
+            roofline["projection"] = {"TFLOPs": tf, "dmma_peak": 37.1, "frac": tf / 37.1, "Nmom": len(mom),
+                                      "bound": "tensor" if len(mom) >= 12 else "hbm",
+                                      "peak_source": "measured DMMA stream, tools/microbench.cu"}
 
     # ---- leg 2: end to end through the public API with HOST buffers -----------------------------------------
     e2e = None
