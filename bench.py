@@ -342,6 +342,7 @@ def run_ours(args, wl, name):
     sampler = ClockSampler(physical_device_index(local_rank))
     ms_step = timed(step_resident, args.steps, args.warmup, sampler)
     halo_sides = getattr(loop, "tsplit_halo_sides", 2)
+    halo_slices = getattr(loop, "tsplit_halo_slices", 2 * ts.H if ts is not None else 0)
     if ts is not None and getattr(loop, "_trace_on", False):
         torch.cuda.synchronize()
         print(f"[rank {rank}] T-split phases of the last step (device ms, host ms): " +
@@ -462,9 +463,9 @@ def run_ours(args, wl, name):
                            "l2": f"inputs larger than L2 ({nev * V4 * 192 / 1e9:.2f} GB of eigenvectors read per step)",
                            "evec_batch": args.evec_batch,
                            "partition": ("lattice-T split, global T = %d, halo %d slices, %.1f MB of halo per rank and step over "
-                                         "NVLink (%d-sided eigenvector halo, transport %s; interior-only compute)"
-                                         % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector(sides=halo_sides) / 1e6, halo_sides,
-                                            args.halo))
+                                         "NVLink (%d-sided eigenvector halo of %d slice(s), transport %s; interior-only compute)"
+                                         % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector(slices=halo_slices) / 1e6, halo_sides,
+                                            halo_slices, args.halo))
                            if ts is not None else ("eigenvector shards" if world > 1 else "single GPU")},
                 "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "quda_order": quda, "gpu_launches": launches,
                 "clocks": sampler.summary()}

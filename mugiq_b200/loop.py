@@ -290,7 +290,8 @@ class Loop_Mugiq:
         plan.set_t_range(ts.H, ts.H + ts.Tl)
         lo, up, ll = plan.t_halo()
         self.tsplit_halo_sides = int(lo > 0) + int(up > 0)
-        ext_kw = dict(group=self.group, device=self.device, lower=lo > 0, upper=up > 0)
+        self.tsplit_halo_slices = lo + up  # only the slices that are read travel (H is rounded up to even)
+        ext_kw = dict(group=self.group, device=self.device, lower=lo, upper=up)
         # the halo exchange of batch i+1 is posted before the kernels of batch i are launched, so it overlaps them
         pending = ts.begin_extend(es.eVecs[batches[0][0]:batches[0][1]], **ext_kw)
         for i, (b0, b1) in enumerate(batches):
@@ -316,7 +317,7 @@ class Loop_Mugiq:
                 if d == 3 and sgn == 1:
                     slots += list(range(iL, iL + b - a + 1))
                 iL += b - a + 1
-            ts.exchange_loop_halo(self.dataPosExt_d, slots, group=self.group)
+            ts.exchange_loop_halo(self.dataPosExt_d, slots, group=self.group, depth=ll)
             self._mark("loop halo")
         plan.finalize(self.dataPosExt_d)
         self._mark("finalize")

@@ -86,10 +86,11 @@ class TSplit:
         cur = torch.cuda.current_stream(slabs.device)
         pr["stream"].wait_stream(cur)  # the interiors are final
         with torch.cuda.stream(pr["stream"]):
-            if upper:  # my first H interior slices are the upper halo of the rank below
-                ops.halo_push_t(pr["dn"], slabs.data_ptr(), first, nb, Lt_ext, self.V3h, H, H + Tl, H, pr["mode"], site_bytes)
-            if lower:  # my last H interior slices are the lower halo of the rank above
-                ops.halo_push_t(pr["up"], slabs.data_ptr(), first, nb, Lt_ext, self.V3h, Tl, 0, H, pr["mode"], site_bytes)
+            if upper:  # my first `upper` interior slices are the upper halo of the rank below
+                ops.halo_push_t(pr["dn"], slabs.data_ptr(), first, nb, Lt_ext, self.V3h, H, H + Tl, upper, pr["mode"], site_bytes)
+            if lower:  # my last `lower` interior slices are the lower halo of the rank above
+                ops.halo_push_t(pr["up"], slabs.data_ptr(), first, nb, Lt_ext, self.V3h, H + Tl - lower, H - lower, lower,
+                                pr["mode"], site_bytes)
             if self.world > 1 and (lower or upper):
                 dist.all_reduce(pr["flag"], group=pr["group"])  # every rank's pushes precede its contribution
             ev = torch.cuda.Event()
@@ -126,17 +127,19 @@ class TSplit:
     def begin_extend(self, vectors, group=None, device=None, lower=True, upper=True):
         """Starts the extension of a batch of eigenvectors (sequence of [V4_loc, 12] tensors in local even/odd order, or
         one [nb, V4_loc, 12] tensor): the interiors are written into the extended buffer and the halo send/recv pairs are
-        posted (asynchronously: they overlap whatever is launched before finish_extend).  `lower` / `upper`: which halos
-        the kernels will read (LoopPlan.t_halo(): plus-t loops read above the interior, directly computed minus-t loops
-        below it; a halo nobody reads is neither sent nor filled).  Every rank must pass the same flags.
-        Returns a handle."""
+        posted (asynchronously: they overlap whatever is launched before finish_extend).  `lower` / `upper`: how many halo
+        slices below / above the interior the kernels will read (True = all H; LoopPlan.t_halo(): plus-t loops of length
+        k read k slices above the interior, directly computed minus-t loops below it; H itself is rounded up to even for
+        the parity bookkeeping, but only the slices that are read are sent and filled).  Every rank must pass the same
+        values.  Returns a handle."""
         import torch.distributed as dist
         nb = len(vectors)
         H, Tl = self.H, self.Tl
         v0 = vectors[0]
         device = device if device is not None else v0.device
         ncomp = 12
-        lower, upper = bool(lower) and H > 0, bool(upper) and H > 0
+        lower = H if lower is True else min(int(lower), H)
+        upper = H if upper is True else min(int(upper), H)
         if self.peer is not None and v0.numel() == 2 * (Tl + 2 * H) * self.V3h * ncomp:
             return self._begin_extend_peer(vectors, lower, upper)
         top = bot = None
@@ -145,26 +148,27 @@ class TSplit:
             # halos move, nothing is copied
             views = [v.reshape(2, Tl + 2 * H, self.V3h, ncomp) for v in vectors]
             batch = _as_batch(views)  # one strided view when the fields are slices of one allocation: 2 copies, not 2*nb
-            h = {"ext": None, "views": views, "batch": batch, "reqs": [], "from_dn": None, "from_up": None}
+            h = {"ext": None, "views": views, "batch": batch, "reqs": [], "from_dn": None, "from_up": None,
+                 "lower": lower, "upper": upper}
             if batch is not None:
                 if lower:
-                    top = batch[:, :, Tl:Tl + H].contiguous()
+                    top = batch[:, :, H + Tl - lower:H + Tl].contiguous()
                 if upper:
-                    bot = batch[:, :, H:2 * H].contiguous()
+                    bot = batch[:, :, H:H + upper].contiguous()
             else:
                 if lower:
-                    top = torch.stack([v[:, Tl:Tl + H] for v in views])
+                    top = torch.stack([v[:, H + Tl - lower:H + Tl] for v in views])
                 if upper:
-                    bot = torch.stack([v[:, H:2 * H] for v in views])
+                    bot = torch.stack([v[:, H:H + upper] for v in views])
         else:
             ext = torch.empty((nb, 2, Tl + 2 * H, self.V3h, ncomp), dtype=v0.dtype, device=device)
             for k in range(nb):
                 ext[k, :, H:H + Tl].copy_(vectors[k].reshape(2, Tl, self.V3h, ncomp), non_blocking=True)
-            h = {"ext": ext, "views": None, "reqs": [], "from_dn": None, "from_up": None}
+            h = {"ext": ext, "views": None, "reqs": [], "from_dn": None, "from_up": None, "lower": lower, "upper": upper}
             if lower:
-                top = ext[:, :, Tl:Tl + H].contiguous()  # owned slices Tl-H..Tl-1: the LOWER halo of the rank above
+                top = ext[:, :, H + Tl - lower:H + Tl].contiguous()  # last owned slices: the LOWER halo of the rank above
             if upper:
-                bot = ext[:, :, H:2 * H].contiguous()    # owned slices 0..H-1: the UPPER halo of the rank below
+                bot = ext[:, :, H:H + upper].contiguous()            # first owned slices: the UPPER halo of the rank below
         if lower or upper:
             if self.world == 1:
                 h["from_dn"], h["from_up"] = top, bot
@@ -190,27 +194,28 @@ class TSplit:
             return h["views"]
         for req in h["reqs"]:
             req.wait()
+        lo, up = h["lower"], h["upper"]
         if h["views"] is not None:
             if h["batch"] is not None:
                 if h["from_dn"] is not None:
-                    h["batch"][:, :, :H] = h["from_dn"]
+                    h["batch"][:, :, H - lo:H] = h["from_dn"]
                 if h["from_up"] is not None:
-                    h["batch"][:, :, H + Tl:] = h["from_up"]
+                    h["batch"][:, :, H + Tl:H + Tl + up] = h["from_up"]
             else:
                 for k, v in enumerate(h["views"]):
                     if h["from_dn"] is not None:
-                        v[:, :H] = h["from_dn"][k]
+                        v[:, H - lo:H] = h["from_dn"][k]
                     if h["from_up"] is not None:
-                        v[:, H + Tl:] = h["from_up"][k]
+                        v[:, H + Tl:H + Tl + up] = h["from_up"][k]
             return [v.reshape(2 * (Tl + 2 * H) * self.V3h, -1) for v in h["views"]]
         ext = h["ext"]
         if h["from_dn"] is not None:
-            ext[:, :, :H] = h["from_dn"]
+            ext[:, :, H - lo:H] = h["from_dn"]
         if h["from_up"] is not None:
-            ext[:, :, H + Tl:] = h["from_up"]
+            ext[:, :, H + Tl:H + Tl + up] = h["from_up"]
         return ext.reshape(ext.shape[0], 2 * (Tl + 2 * H) * self.V3h, -1)
 
-    def exchange_loop_halo(self, dataPosExt, slots, group=None):
+    def exchange_loop_halo(self, dataPosExt, slots, group=None, depth=None):
         """Fills the LOWER halo slices of the given loop slots of the extended position-space buffer
         [nLoop, 16, V4_ext] with the top interior slices of the rank below (periodic).  A minus-t loop derived from its
         plus-t partner reads the partner at x - k t: for the first k interior slices that is the neighbour's interior,
@@ -218,7 +223,8 @@ class TSplit:
         eigenvector halo (and its contraction) per eigenvector."""
         import torch.distributed as dist
         H, Tl = self.H, self.Tl
-        if H == 0 or len(slots) == 0:
+        d = H if depth is None else min(int(depth), H)  # slices the derived loops read below the interior
+        if d == 0 or len(slots) == 0:
             return
         v = dataPosExt.reshape(dataPosExt.shape[0], dataPosExt.shape[1], 2, Tl + 2 * H, self.V3h)
         slots = sorted(int(x) for x in slots)
@@ -228,7 +234,7 @@ class TSplit:
             if k == len(slots) or slots[k] != slots[k - 1] + 1:
                 runs.append((slots[a], slots[k - 1] + 1))
                 a = k
-        send = torch.cat([v[a:b, :, :, Tl:Tl + H] for a, b in runs]).contiguous()
+        send = torch.cat([v[a:b, :, :, H + Tl - d:H + Tl] for a, b in runs]).contiguous()
         if self.world == 1:
             recv = send
         else:
@@ -238,7 +244,7 @@ class TSplit:
                 req.wait()
         o = 0
         for a, b in runs:
-            v[a:b, :, :, :H] = recv[o:o + b - a]
+            v[a:b, :, :, H - d:H] = recv[o:o + b - a]
             o += b - a
 
     def extend(self, interior, group=None):
@@ -246,9 +252,10 @@ class TSplit:
         world == 1: the halos are the rank's own far slices (plain periodic lattice)."""
         return self.finish_extend(self.begin_extend(interior, group=group))
 
-    def halo_bytes_per_vector(self, itemsize=16, sides=2):
-        """bytes one eigenvector sends (= receives) per extension: `sides` neighbours x H slices x V3 sites x 12 complex"""
-        return sides * self.H * 2 * self.V3h * 12 * itemsize
+    def halo_bytes_per_vector(self, itemsize=16, slices=None):
+        """bytes one eigenvector sends (= receives) per extension: `slices` time-slices (default: H to each of the two
+        neighbours) x V3 sites x 12 complex"""
+        return (2 * self.H if slices is None else slices) * 2 * self.V3h * 12 * itemsize
 
     def gather_time(self, local_mom, group=None):
         """[Nmom, nData, Tl] per rank -> [Nmom, nData, T] on every rank (COMM_TIME gather + broadcast of the reference)."""

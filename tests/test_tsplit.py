@@ -106,6 +106,9 @@ def _worker(rank, world, port, out_dir):
     full = ts.global_slab(g, site_dim=1).reshape(-1, 2, ts.Tl + 2 * ts.H, ts.V3h, 12)
     got = up_only.reshape(full.shape)
     ok = ok and torch.equal(got[:, :, ts.H:], full[:, :, ts.H:])
+    # exactly the slices that are read: one above, one below (H = 2 is only the parity-preserving offset)
+    part = ts.finish_extend(ts.begin_extend(inner, group=dist.group.WORLD, lower=1, upper=1)).reshape(full.shape)
+    ok = ok and torch.equal(part[:, :, ts.H - 1:ts.H + ts.Tl + 1], full[:, :, ts.H - 1:ts.H + ts.Tl + 1])
     # loop-buffer halo: the lower halo slices of the chosen slots become the top interior slices of the rank below
     rng = np.random.default_rng(7)
     V4g = int(np.prod(L))
@@ -113,8 +116,10 @@ def _worker(rank, world, port, out_dir):
     pos_ext = ts.global_slab(pos_g, site_dim=2).clone()
     pv = pos_ext.reshape(4, 16, 2, ts.Tl + 2 * ts.H, ts.V3h)
     pv[:, :, :, :ts.H] = 0
-    ts.exchange_loop_halo(pos_ext, [1, 3], group=dist.group.WORLD)
+    ts.exchange_loop_halo(pos_ext, [1, 3], group=dist.group.WORLD, depth=1)
     want_ext = ts.global_slab(pos_g, site_dim=2).reshape(pv.shape)
+    ok = ok and torch.equal(pv[[1, 3]][:, :, :, ts.H - 1:ts.H], want_ext[[1, 3]][:, :, :, ts.H - 1:ts.H]) and bool((pv[[1, 3]][:, :, :, :ts.H - 1] == 0).all())
+    ts.exchange_loop_halo(pos_ext, [1, 3], group=dist.group.WORLD)
     ok = ok and torch.equal(pv[[1, 3]][:, :, :, :ts.H], want_ext[[1, 3]][:, :, :, :ts.H]) and bool((pv[[0, 2]][:, :, :, :ts.H] == 0).all())
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
     dist.destroy_process_group()
@@ -128,7 +133,7 @@ def test_halo_exchange_gloo(tmp_path, world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("sides", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("sides", [(True, True), (False, True), (True, False), (1, 1)])
 def test_peer_halo_push_single_rank(mode, sides):
     """NVLink peer mode with one rank: the 'neighbours' are the rank's own allocation, so the pushed halos must be the
     periodic wrap - by the copy engines (mode 0) and by the SM push kernel (mode 1), for a batch in the middle of the
@@ -150,10 +155,12 @@ def test_peer_halo_push_single_rank(mode, sides):
         torch.cuda.synchronize()
         assert len(out) == 3 and out[0].data_ptr() == slabs[1].data_ptr()
         w = want.reshape(v.shape)
-        assert torch.equal(v[1:4, :, ts.H:ts.H + ts.Tl], w[1:4, :, ts.H:ts.H + ts.Tl])
-        assert torch.equal(v[1:4, :, :ts.H], w[1:4, :, :ts.H]) if lower else bool((v[1:4, :, :ts.H] == 7.0).all())
-        assert torch.equal(v[1:4, :, ts.H + ts.Tl:], w[1:4, :, ts.H + ts.Tl:]) if upper else bool((v[1:4, :, ts.H + ts.Tl:] == 7.0).all())
-        assert bool((v[0, :, :ts.H] == 7.0).all()) and bool((v[4, :, ts.H + ts.Tl:] == 7.0).all())  # other vectors untouched
+        H, Tl = ts.H, ts.Tl
+        lo = H if lower is True else int(lower)
+        up = H if upper is True else int(upper)
+        assert torch.equal(v[1:4, :, H - lo:H + Tl + up], w[1:4, :, H - lo:H + Tl + up])       # interior + the requested slices
+        assert bool((v[1:4, :, :H - lo] == 7.0).all()) and bool((v[1:4, :, H + Tl + up:] == 7.0).all())  # nothing else written
+        assert bool((v[0, :, :H] == 7.0).all()) and bool((v[4, :, H + Tl:] == 7.0).all())     # other vectors untouched
     finally:
         del slabs, v
         buf.free()
@@ -227,18 +234,20 @@ def test_tsplit_loop_matches_global_oracle(oracle, world, symmetric, monkeypatch
             n, lower, upper = h
             ext = ts.global_slab(evg[:n], site_dim=1).clone()
             v = ext.reshape(n, 2, ts.Tl + 2 * H, ts.V3h, 12)
-            if not lower:
-                v[:, :, :H] = float("nan")  # a halo the plan said it does not read must not influence the result
-            if not upper:
-                v[:, :, H + ts.Tl:] = float("nan")
+            # halo slices the plan said it does not read must not influence the result
+            lo = H if lower is True else int(lower)
+            up = H if upper is True else int(upper)
+            v[:, :, :H - lo] = float("nan")
+            v[:, :, H + ts.Tl + up:] = float("nan")
             return ext
 
-        def loop_halo(dataPosExt, slots, group=None):
+        def loop_halo(dataPosExt, slots, group=None, depth=None):
+            d = H if depth is None else int(depth)
             v = dataPosExt.reshape(dataPosExt.shape[0], 16, 2, ts.Tl + 2 * H, ts.V3h)
             idx = torch.as_tensor(list(slots), device=dataPosExt.device)
-            sent[rank] = v[idx][:, :, :, ts.Tl:ts.Tl + H].clone()
+            sent[rank] = v[idx][:, :, :, H + ts.Tl - d:H + ts.Tl].clone()
             if deliver:
-                v[idx, :, :, :H] = sent[(rank - 1) % world]
+                v[idx, :, :, H - d:H] = sent[(rank - 1) % world]
 
         monkeypatch.setattr(ts, "begin_extend", begin)
         monkeypatch.setattr(ts, "finish_extend", finish)
