@@ -20,8 +20,18 @@ int mugiqCommRank(const MugiqComm *comm);
 int mugiqCommSize(const MugiqComm *comm);
 // In-place sum of `count` real numbers of the given precision over all ranks (device buffer); returns when done.
 void mugiqCommAllReduceSum(MugiqComm *comm, void *buf_d, size_t count, QudaPrecision prec);
+// Lattice-T split (tsplit in loop_mugiq.cpp): every rank contributes `bytes` bytes (device buffers), rank-major result.
+void mugiqCommAllGather(MugiqComm *comm, const void *send_d, void *recv_d, size_t bytes);
+// Stream-ordered barrier: a one-element all-reduce enqueued on `stream` (cudaStream_t as void*); work enqueued on that
+// stream afterwards starts only when every rank's earlier work on ITS stream has finished.  No host synchronisation.
+void mugiqCommStreamBarrier(MugiqComm *comm, void *stream);
 // eigenvector shard [lo, hi) of rank r: contiguous blocks whose sizes differ by at most one
 void mugiqCommShard(int nEv, int rank, int size, int *lo, int *hi);
+
+// Lattice-T split: Loop_Mugiq treats the eigenvectors as this rank's time slab of a lattice with comm_dim(3) slabs
+// (communicator = getLoopComm(), all of whose ranks are time ranks; one rank = periodic in its own slab).
+void setLoopTSplit(bool on);
+bool getLoopTSplit();
 
 // The communicator Loop_Mugiq sums its loop buffer over (nullptr = single process).
 void setLoopComm(MugiqComm *comm);

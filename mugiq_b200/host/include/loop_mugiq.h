@@ -34,6 +34,7 @@ template <typename Float, QudaFieldOrder fieldOrder> class Loop_Mugiq {
   void *momWorkspace_d = nullptr;
   bool fusedMomProj = true;                 // stages 3+4 as one kernel on dataPos_d (no dataPosMP_d)
   void *evecStage_d = nullptr;  // site-major staging for QUDA-native eigenvectors
+  const void *gaugeHost[4] = {nullptr, nullptr, nullptr, nullptr};  // borrowed (MugiqLoopParam::gauge): the T split cuts its slab
 
   const size_t SizeCplxFloat = sizeof(complex<Float>);
   long long nElemMomTotPerLoop, nElemMomLocPerLoop, nElemPosLocPerLoop;
@@ -50,6 +51,7 @@ template <typename Float, QudaFieldOrder fieldOrder> class Loop_Mugiq {
   void copyGammaToConstMem();
   void createPhaseMatrix();
   void performMomentumProjection();
+  void computeCoarseLoopTSplit();  // the eigenvectors are this rank's time slab (comm_dim(3) > 1 or setLoopTSplit)
   void writeLoopsHDF5_Mom();
   void writeLoopsHDF5_Pos();
 

@@ -70,9 +70,24 @@ void setVerbosityQuda(QudaVerbosity v);
 #define warningQuda(...) ::quda::warningQuda_(__VA_ARGS__)
 #define printfQuda(...) ::quda::printfQuda_(__VA_ARGS__)
 
-// single process: the hot path shards eigenvectors, not the lattice
-inline int comm_dim(int) { return 1; }
-inline int comm_coord(int) { return 0; }
+// The hot path shards eigenvectors, not the lattice; the one lattice partitioning it knows is the split in t
+// (secondary partitioning), which the driver announces with setTimePartition(size, coord).
+namespace detail {
+inline int &time_ranks() {
+  static int v = 1;
+  return v;
+}
+inline int &time_coord() {
+  static int v = 0;
+  return v;
+}
+}  // namespace detail
+inline void setTimePartition(int size, int coord) {
+  detail::time_ranks() = size;
+  detail::time_coord() = coord;
+}
+inline int comm_dim(int d) { return d == 3 ? detail::time_ranks() : 1; }
+inline int comm_coord(int d) { return d == 3 ? detail::time_coord() : 0; }
 inline int comm_rank() { return 0; }
 inline int comm_size() { return 1; }
 

@@ -14,6 +14,7 @@ struct MugiqComm {
   int rank, size;
   ncclComm_t nccl;
   cudaStream_t stream;
+  float *flag_d = nullptr;  // operand of the stream barrier
 };
 
 #define NCCL_CHECK(expr)                                                             \
@@ -55,6 +56,7 @@ MugiqComm *mugiqCommInit(int rank, int size, int device, const char *id_file) {
 void mugiqCommFinalize(MugiqComm *c) {
   if (!c) return;
   cudaStreamSynchronize(c->stream);
+  if (c->flag_d) cudaFree(c->flag_d);
   ncclCommDestroy(c->nccl);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -70,11 +72,34 @@ void mugiqCommAllReduceSum(MugiqComm *c, void *buf_d, size_t count, QudaPrecisio
   HOST_CUDA(cudaStreamSynchronize(c->stream));
 }
 
+void mugiqCommAllGather(MugiqComm *c, const void *send_d, void *recv_d, size_t bytes) {
+  if (!c || c->size == 1) {
+    HOST_CUDA(cudaMemcpy(recv_d, send_d, bytes, cudaMemcpyDeviceToDevice));
+    return;
+  }
+  HOST_CUDA(cudaDeviceSynchronize());
+  NCCL_CHECK(ncclAllGather(send_d, recv_d, bytes, ncclChar, c->nccl, c->stream));
+  HOST_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void mugiqCommStreamBarrier(MugiqComm *c, void *stream) {
+  if (!c || c->size == 1) return;
+  if (!c->flag_d) {
+    HOST_CUDA(cudaMalloc((void **)&c->flag_d, sizeof(float)));
+    HOST_CUDA(cudaMemset(c->flag_d, 0, sizeof(float)));
+  }
+  NCCL_CHECK(ncclAllReduce(c->flag_d, c->flag_d, 1, ncclFloat, ncclSum, c->nccl, (cudaStream_t)stream));
+}
+
 void mugiqCommShard(int nEv, int rank, int size, int *lo, int *hi) {
   const int base = nEv / size, rem = nEv % size;
   *lo = rank * base + (rank < rem ? rank : rem);
   *hi = *lo + base + (rank < rem ? 1 : 0);
 }
+
+static bool g_loop_tsplit = false;
+void setLoopTSplit(bool on) { g_loop_tsplit = on; }
+bool getLoopTSplit() { return g_loop_tsplit; }
 
 static MugiqComm *g_loop_comm = nullptr;
 void setLoopComm(MugiqComm *comm) { g_loop_comm = comm; }

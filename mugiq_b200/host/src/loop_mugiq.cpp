@@ -99,6 +99,7 @@ Loop_Mugiq<Float, fieldOrder>::Loop_Mugiq(MugiqLoopParam *loopParams_, Eigsolve_
   if (refVec->FieldOrder() != fieldOrder) errorQuda("%s: eigenvector field order %d does not match the template", __func__, (int)refVec->FieldOrder());
 
   cPrm = new LoopComputeParam(loopParams_, refVec);
+  for (int mu = 0; mu < 4; mu++) gaugeHost[mu] = loopParams_->gauge[mu];
   setupComms();
   allocateDataMemory();
   copyGammaToConstMem();
@@ -213,6 +214,10 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
     errorQuda("%s: singular values are only defined for MdagM / MMdag eigensolves and are required here", __func__);
   const QudaPrecision evecPrec = eigsolve->eVecs[0]->Precision();
   if (evecPrec != precision_of<Float>()) errorQuda("%s: Precision not supported!", __func__);
+  if (getLoopTSplit()) {
+    computeCoarseLoopTSplit();
+    return;
+  }
   const mugiq_b200_geom_t geom = make_geom(cPrm->localL, precision_of<Float>());
 
   // entries in the order given; directions parsed exactly as Displace does for the hop-by-hop interface
@@ -273,6 +278,185 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
 
   if (cPrm->doMomProj) {
     performMomentumProjection();
+    printfQuda("%s: Momentum projection completed\n", __func__);
+  }
+}
+
+// Lattice partitioned in t (the reference's comm_dim(3) > 1, SURVEY §8e secondary partitioning): the eigenvectors are this
+// rank's time slab.  Replaces the per-hop exchangeGhostVec + ghost-zone reads (lib/contract_wrappers.cu:166-174,
+// lib/mugiq_displace_kernels.cu:116-151) and the extended gauge field (lib/displace.cpp:104-134): the slabs are copied once
+// into the extended layout [vector][parity][t = 0 .. Tl+2H)[V3/2][12] in an allocation the two time neighbours map through
+// CUDA IPC; per eigenvector batch the boundary slices are written straight into the neighbours' halo slices over NVLink
+// (copy engines), the kernels compute the interior only, and a minus-t loop derived from its plus partner fetches the
+// partner's loop values below the interior from the neighbour once, after the eigenvector sum.
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::computeCoarseLoopTSplit() {
+  if (fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER || sizeof(Float) != 8)
+    errorQuda("%s: the lattice-T split of this build takes site-major double-precision eigenvectors", __func__);
+  MugiqComm *comm = getLoopComm();
+  const int world = comm_dim(3), rank = comm_coord(3);
+  if (world != mugiqCommSize(comm) || (world > 1 && rank != mugiqCommRank(comm)))
+    errorQuda("%s: %d time ranks announced but the communicator has %d", __func__, world, mugiqCommSize(comm));
+  const int nEv = eigsolve->eigParams->nEv;
+  const int Tl = cPrm->localL[3], T = cPrm->totalL[3];
+  std::vector<mugiq_b200_disp_entry_t> entries;
+  int tmax = 0;
+  for (int id = 0; id < cPrm->nDispEntries; id++) {
+    displace->setupDisplacement(cPrm->dispString[id]);
+    entries.push_back({(int)displace->dispDir, (int)displace->dispSign, cPrm->dispStart[id], cPrm->dispStop[id]});
+    if ((int)displace->dispDir == 3) tmax = std::max(tmax, cPrm->dispStop[id]);
+  }
+  const int H = tmax + (tmax & 1);  // even: a site keeps its parity in local, extended and global coordinates
+  if (Tl % 2) errorQuda("%s: local T = %d must be even", __func__, Tl);
+  if (H > Tl) errorQuda("%s: t-displacements of length %d exceed the local time extent %d", __func__, tmax, Tl);
+  const int LtE = Tl + 2 * H;
+  int Lext[4] = {cPrm->localL[0], cPrm->localL[1], cPrm->localL[2], LtE};
+  const mugiq_b200_geom_t geomE = make_geom(Lext, precision_of<Float>());
+  const size_t V3h = (size_t)cPrm->locV3 / 2, V4e = 2 * (size_t)LtE * V3h;
+  const size_t S = 12 * SizeCplxFloat, U = 9 * SizeCplxFloat;
+
+  // links of the extended slab, cut from the replicated global host field
+  void *gaugeE_d = nullptr;
+  if (cPrm->doNonLocal) {
+    std::vector<char> slab(4 * V4e * U);
+    const void *ptrs[4];
+    for (int mu = 0; mu < 4; mu++) {
+      if (!gaugeHost[mu]) errorQuda("%s: MugiqLoopParam::gauge[%d] is not set", __func__, mu);
+      ptrs[mu] = slab.data() + (size_t)mu * V4e * U;
+      for (int p = 0; p < 2; p++)
+        for (int te = 0; te < LtE; te++) {
+          const int tg = ((rank * Tl - H + te) % T + T) % T;
+          memcpy(slab.data() + ((size_t)mu * V4e + ((size_t)p * LtE + te) * V3h) * U,
+                 static_cast<const char *>(gaugeHost[mu]) + ((size_t)p * T + tg) * V3h * U, V3h * U);
+        }
+    }
+    HOST_CUDA(cudaMalloc(&gaugeE_d, 4 * V4e * U));
+    MUGIQ_CHECK(mugiq_b200_gauge_upload(gaugeE_d, ptrs, &geomE, nullptr));
+  }
+
+  // eigenvector slabs and the loop buffer in the extended layout, in allocations the neighbours can map
+  void *slabs_d = nullptr, *posE_d = nullptr;
+  char hSlabs[64], hPos[64];
+  const size_t posBytes = (size_t)cPrm->nLoop * 16 * V4e * SizeCplxFloat;
+  MUGIQ_CHECK(mugiq_b200_peer_alloc(&slabs_d, (long long)(nEv * V4e * S), hSlabs));
+  MUGIQ_CHECK(mugiq_b200_peer_alloc(&posE_d, (long long)posBytes, hPos));
+  HOST_CUDA(cudaMemset(posE_d, 0, posBytes));
+  for (int n = 0; n < nEv; n++)
+    for (int p = 0; p < 2; p++)
+      HOST_CUDA(cudaMemcpyAsync(static_cast<char *>(slabs_d) + ((size_t)n * V4e + ((size_t)p * LtE + H) * V3h) * S,
+                                static_cast<const char *>(eigsolve->eVecs[n]->V()) + (size_t)p * Tl * V3h * S, (size_t)Tl * V3h * S,
+                                cudaMemcpyDeviceToDevice, nullptr));
+  void *upSlabs = slabs_d, *dnSlabs = slabs_d, *upPos = posE_d;
+  if (world > 1) {
+    char *send_d = nullptr, *recv_d = nullptr;
+    std::vector<char> all((size_t)128 * world);
+    HOST_CUDA(cudaMalloc((void **)&send_d, 128));
+    HOST_CUDA(cudaMalloc((void **)&recv_d, (size_t)128 * world));
+    char mine[128];
+    memcpy(mine, hSlabs, 64);
+    memcpy(mine + 64, hPos, 64);
+    HOST_CUDA(cudaMemcpy(send_d, mine, 128, cudaMemcpyHostToDevice));
+    mugiqCommAllGather(comm, send_d, recv_d, 128);
+    HOST_CUDA(cudaMemcpy(all.data(), recv_d, all.size(), cudaMemcpyDeviceToHost));
+    cudaFree(send_d);
+    cudaFree(recv_d);
+    const int up = (rank + 1) % world, dn = (rank - 1 + world) % world;
+    MUGIQ_CHECK(mugiq_b200_peer_open(&upSlabs, all.data() + (size_t)128 * up));
+    MUGIQ_CHECK(mugiq_b200_peer_open(&upPos, all.data() + (size_t)128 * up + 64));
+    if (dn == up)
+      dnSlabs = upSlabs;
+    else
+      MUGIQ_CHECK(mugiq_b200_peer_open(&dnSlabs, all.data() + (size_t)128 * dn));
+  }
+
+  mugiq_b200_loop_plan_t *plan = nullptr;
+  MUGIQ_CHECK(mugiq_b200_loop_plan_create(&plan, gaugeE_d, entries.empty() ? nullptr : entries.data(), (int)entries.size(), &geomE, nullptr));
+  if (mugiq_b200_loop_plan_nloop(plan) != cPrm->nLoop) errorQuda("%s: plan holds %d loops, expected %d", __func__, mugiq_b200_loop_plan_nloop(plan), cPrm->nLoop);
+  MUGIQ_CHECK(mugiq_b200_loop_plan_set_t_range(plan, H, H + Tl));  // the kernels compute the interior, the halos are read
+  int lo = 0, up = 0, ll = 0;
+  MUGIQ_CHECK(mugiq_b200_loop_plan_t_halo(plan, &lo, &up, &ll));
+
+  cudaStream_t cs;
+  HOST_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  HOST_CUDA(cudaDeviceSynchronize());  // the interiors are in place on every...
+  mugiqCommStreamBarrier(comm, cs);    // ...rank before anybody writes halos next to them
+  const int batch = std::min(nEv, 128);
+  const int nbatch = (nEv + batch - 1) / batch;
+  std::vector<cudaEvent_t> landed(nbatch);
+  auto push = [&](int b) {  // halo slices of batch b -> the neighbours' slabs, then "everybody's pushes have landed"
+    const int n0 = b * batch, nb = std::min(batch, nEv - n0);
+    if (up) MUGIQ_CHECK(mugiq_b200_halo_push_t(dnSlabs, slabs_d, n0, nb, LtE, (long long)V3h, (int)S, H, H + Tl, up, 0, cs));
+    if (lo) MUGIQ_CHECK(mugiq_b200_halo_push_t(upSlabs, slabs_d, n0, nb, LtE, (long long)V3h, (int)S, H + Tl - lo, H - lo, lo, 0, cs));
+    mugiqCommStreamBarrier(comm, cs);
+    HOST_CUDA(cudaEventCreateWithFlags(&landed[b], cudaEventDisableTiming));
+    HOST_CUDA(cudaEventRecord(landed[b], cs));
+  };
+  push(0);
+  std::vector<const void *> ptr(batch);
+  std::vector<double> sigma(batch);
+  for (int b = 0; b < nbatch; b++) {
+    if (b + 1 < nbatch) push(b + 1);  // overlaps the kernels of batch b
+    const int n0 = b * batch, nb = std::min(batch, nEv - n0);
+    for (int i = 0; i < nb; i++) {
+      ptr[i] = static_cast<const char *>(slabs_d) + (size_t)(n0 + i) * V4e * S;
+      sigma[i] = (double)(Float)(*(eigsolve->eVals_sigma))[n0 + i];
+    }
+    HOST_CUDA(cudaStreamWaitEvent(nullptr, landed[b], 0));
+    MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, posE_d, ptr.data(), sigma.data(), nb, b > 0, nullptr));
+    printfQuda("%s: Loop trace for eigenvectors %04d - %04d completed (time slab %d of %d)\n", __func__, n0, n0 + nb - 1, rank, world);
+  }
+  if (ll > 0) {
+    // derived minus-t loops read their plus partner below the interior: the neighbour's top interior slices of every
+    // plus-t slot, pushed with the same primitive (a loop slot is 16 "vectors" of 16-byte sites)
+    HOST_CUDA(cudaDeviceSynchronize());
+    int iL = 1;
+    for (size_t id = 0; id < entries.size(); id++) {
+      const int n = entries[id].stop - entries[id].start + 1;
+      if (entries[id].dir == 3 && entries[id].sign == 1)
+        for (int k = 0; k < n; k++)
+          MUGIQ_CHECK(mugiq_b200_halo_push_t(upPos, posE_d, (iL + k) * 16, 16, LtE, (long long)V3h, (int)SizeCplxFloat, H + Tl - ll, H - ll, ll, 0, cs));
+      iL += n;
+    }
+    mugiqCommStreamBarrier(comm, cs);
+    HOST_CUDA(cudaStreamSynchronize(cs));
+  }
+  MUGIQ_CHECK(mugiq_b200_loop_plan_finalize(plan, posE_d, 0, nullptr));
+  // the interior of the extended buffer is this rank's dataPos
+  HOST_CUDA(cudaMemcpy2D(dataPos_d, (size_t)Tl * V3h * SizeCplxFloat, static_cast<const char *>(posE_d) + (size_t)H * V3h * SizeCplxFloat,
+                         (size_t)LtE * V3h * SizeCplxFloat, (size_t)Tl * V3h * SizeCplxFloat, (size_t)cPrm->nLoop * 16 * 2, cudaMemcpyDeviceToDevice));
+  HOST_CUDA(cudaMemcpy(dataPos, dataPos_d, SizeCplxFloat * nElemPosLoc, cudaMemcpyDeviceToHost));
+  HOST_CUDA(cudaDeviceSynchronize());
+  mugiqCommStreamBarrier(comm, cs);  // nobody unmaps while a neighbour may still write
+  HOST_CUDA(cudaStreamSynchronize(cs));
+  mugiq_b200_loop_plan_destroy(plan);
+  for (cudaEvent_t e : landed) cudaEventDestroy(e);
+  if (world > 1) {
+    if (dnSlabs != upSlabs) MUGIQ_CHECK(mugiq_b200_peer_close(dnSlabs));
+    MUGIQ_CHECK(mugiq_b200_peer_close(upSlabs));
+    MUGIQ_CHECK(mugiq_b200_peer_close(upPos));
+    mugiqCommStreamBarrier(comm, cs);  // everybody has unmapped before anybody frees
+    HOST_CUDA(cudaStreamSynchronize(cs));
+  }
+  cudaStreamDestroy(cs);
+  MUGIQ_CHECK(mugiq_b200_peer_free(slabs_d));
+  MUGIQ_CHECK(mugiq_b200_peer_free(posE_d));
+  if (gaugeE_d) cudaFree(gaugeE_d);
+  printfQuda("%s: Loop trace completed (time slab %d of %d, halo %d slice(s) up, %d down, loop halo %d)\n", __func__, rank, world, up, lo, ll);
+
+  if (cPrm->doMomProj) {
+    performMomentumProjection();  // this rank's time-slices
+    // MPI_Gather over COMM_TIME + MPI_Bcast (lib/loop_mugiq.cpp:420-424): every rank ends with all T time-slices
+    if (world > 1) {
+      complex<Float> *all_d = nullptr;
+      HOST_CUDA(cudaMalloc((void **)&all_d, SizeCplxFloat * nElemMomLoc * world));
+      mugiqCommAllGather(comm, dataMom_d, all_d, SizeCplxFloat * nElemMomLoc);
+      std::vector<complex<Float>> all((size_t)nElemMomLoc * world);
+      HOST_CUDA(cudaMemcpy(all.data(), all_d, SizeCplxFloat * all.size(), cudaMemcpyDeviceToHost));
+      cudaFree(all_d);
+      const size_t rows = (size_t)cPrm->Nmom * cPrm->nData;  // [im][idata] blocks of Tl (rank) -> T (gathered)
+      for (int r = 0; r < world; r++)
+        for (size_t k = 0; k < rows; k++)
+          memcpy(dataMom_bcast + k * T + (size_t)r * Tl, all.data() + (size_t)r * nElemMomLoc + k * Tl, SizeCplxFloat * Tl);
+    }
     printfQuda("%s: Momentum projection completed\n", __func__);
   }
 }

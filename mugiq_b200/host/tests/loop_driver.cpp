@@ -44,22 +44,37 @@ template <typename Float> static void to_native(std::vector<char> &field, QudaFi
   field.swap(out);
 }
 
-template <typename Float> static int run(std::map<std::string, std::string> &opt, const int X[4], MugiqLoopParam &prm, int nEv,
+template <typename Float> static int run(std::map<std::string, std::string> &opt, const int Xg[4], MugiqLoopParam &prm, int nEv,
                                          QudaFieldOrder order) {
+  // --tsplit N: the files hold the GLOBAL lattice Xg; this rank (--comm-rank, 0 for N = 1) keeps the time slab
+  // [rank*T/N, (rank+1)*T/N) of every eigenvector and the whole (replicated) gauge field
+  const int tsN = opt.count("--tsplit") ? atoi(opt["--tsplit"].c_str()) : 0;
+  const int tsRank = tsN > 1 ? mugiqCommRank(getLoopComm()) : 0;
+  int X[4] = {Xg[0], Xg[1], Xg[2], Xg[3]};
+  if (tsN > 0) {
+    if (order != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER) errorQuda("--tsplit takes site-major eigenvectors");
+    if (Xg[3] % tsN) errorQuda("T = %d is not divisible by %d time ranks", Xg[3], tsN);
+    if (tsN != mugiqCommSize(getLoopComm())) errorQuda("--tsplit %d needs --comm-size %d", tsN, tsN);
+    X[3] = Xg[3] / tsN;
+    setTimePartition(tsN, tsRank);
+    setLoopTSplit(true);
+  }
+  const size_t V4g = (size_t)Xg[0] * Xg[1] * Xg[2] * Xg[3];
   const size_t V4 = (size_t)X[0] * X[1] * X[2] * X[3];
   const QudaPrecision prec = precision_of<Float>();
+  const size_t fieldBytesG = V4g * 24 * sizeof(Float);
   const size_t fieldBytes = V4 * 24 * sizeof(Float);
-  std::vector<char> ev = slurp(opt["--evecs-file"], fieldBytes * nEv);
+  std::vector<char> ev = slurp(opt["--evecs-file"], fieldBytesG * nEv);
   std::vector<char> sg = slurp(opt["--sigma-file"], sizeof(double) * nEv);
   std::vector<double> sigma(nEv);
   memcpy(sigma.data(), sg.data(), sg.size());
   std::vector<char> gauge;
   QudaGaugeParam gp;
   if (prm.doNonLocal) {
-    gauge = slurp(opt["--gauge-file"], 4 * V4 * 18 * sizeof(Float));
+    gauge = slurp(opt["--gauge-file"], 4 * V4g * 18 * sizeof(Float));
     for (int i = 0; i < 4; i++) {
       gp.X[i] = X[i];
-      prm.gauge[i] = gauge.data() + (size_t)i * V4 * 18 * sizeof(Float);
+      prm.gauge[i] = gauge.data() + (size_t)i * V4g * 18 * sizeof(Float);
     }
     gp.cpu_prec = gp.cuda_prec = prec;
     gp.gauge_order = QUDA_QDP_GAUGE_ORDER;
@@ -67,7 +82,7 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
   }
   // eigenvector shards: this rank keeps [lo, hi) of the file's eigenpairs
   int lo = 0, hi = nEv;
-  if (getLoopComm()) mugiqCommShard(nEv, mugiqCommRank(getLoopComm()), mugiqCommSize(getLoopComm()), &lo, &hi);
+  if (getLoopComm() && tsN == 0) mugiqCommShard(nEv, mugiqCommRank(getLoopComm()), mugiqCommSize(getLoopComm()), &lo, &hi);
   if (hi <= lo) errorQuda("rank %d got an empty eigenvector shard (%d eigenvectors over %d ranks)", mugiqCommRank(getLoopComm()), nEv, mugiqCommSize(getLoopComm()));
   {
     std::vector<double> shard(sigma.begin() + lo, sigma.begin() + hi);
@@ -79,7 +94,16 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
   cs.precision = prec;
   cs.fieldOrder = order;
   for (int n = lo; n < hi; n++) {
-    std::vector<char> one(ev.begin() + n * fieldBytes, ev.begin() + (n + 1) * fieldBytes);
+    std::vector<char> one;
+    if (tsN > 0) {  // this rank's time-slices of both parities (a time-slice is one contiguous block per parity)
+      const size_t V3h = (size_t)X[0] * X[1] * X[2] / 2, slice = V3h * 24 * sizeof(Float);
+      one.resize(fieldBytes);
+      for (int p = 0; p < 2; p++)
+        memcpy(one.data() + (size_t)p * X[3] * slice, ev.data() + n * fieldBytesG + ((size_t)p * Xg[3] + (size_t)tsRank * X[3]) * slice,
+               (size_t)X[3] * slice);
+    } else {
+      one.assign(ev.begin() + n * fieldBytes, ev.begin() + (n + 1) * fieldBytes);
+    }
     to_native<Float>(one, order, V4 / 2);
     fields.push_back(ColorSpinorField::Create(cs));
     HOST_CUDA(cudaMemcpy(fields.back()->V(), one.data(), fieldBytes, cudaMemcpyHostToDevice));
@@ -178,6 +202,7 @@ int main(int argc, char **argv) {
   if (prec == "double") rc = run<double>(opt, X, prm, nEv, order);
   else if (prec == "single") rc = run<float>(opt, X, prm, nEv, order);
   else errorQuda("Unknown --prec %s (double/single)", prec.c_str());
+  setLoopTSplit(false);
   setLoopComm(nullptr);
   mugiqCommFinalize(comm);
   return rc;

@@ -162,6 +162,70 @@ def test_driver_eigenvector_shards_over_nccl(driver, oracle, tmp_path):
         assert rel_err(pos, ref) < TOL_F64 and rel_err(dm, ref_mom) < TOL_F64
 
 
+def _stitch_time_slabs(parts, ref_shape, L, world):
+    """[rank] local dataPos [nLoop, 16, V4_loc] (even/odd order of the slab) -> global [nLoop, 16, V4]"""
+    V3h, Tl = L[0] * L[1] * L[2] // 2, L[3] // world
+    return np.concatenate([p.reshape(ref_shape[0], 16, 2, Tl, V3h) for p in parts], axis=3).reshape(ref_shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("entry_str,entries", [("+t:1,2;-t:1,2;+x:1;-y:2", [(3, 1, 1, 2), (3, 0, 1, 2), (0, 1, 1, 1), (1, 0, 2, 2)]),
+                                               ("-t:1;+z:1", [(3, 0, 1, 1), (2, 1, 1, 1)])])
+def test_driver_time_split_single_rank(driver, oracle, tmp_path, entry_str, entries):
+    """C++ Loop_Mugiq on a lattice 'partitioned' in t over one rank: extended slabs in a peer allocation, halo pushes into
+    itself (periodic), interior-only kernels, loop-buffer halo of the derived minus-t loops - against the oracle."""
+    from oracle import numpy_check as npc
+    from mugiq_b200.params import momenta_up_to
+    L, nEv = (4, 4, 2, 8), 5
+    ev, U, sig = _inputs(tmp_path, L, nEv, "double")
+    mom = momenta_up_to(1)
+    (tmp_path / "mom.txt").write_text("".join(f"{p[0]} {p[1]} {p[2]}\n" for p in mom))
+    r = run(driver, "--dim", *L, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file", tmp_path / "sig.bin",
+            "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string", entry_str,
+            "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--tsplit", 1,
+            "--dump-pos", tmp_path / "pos.bin", "--dump-mom", tmp_path / "mom.bin")
+    assert r.returncode == 0, r.stderr
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    ref_mom = npc.momentum_projection(ref, mom, -1, L)
+    assert rel_err(np.fromfile(tmp_path / "pos.bin", dtype=np.complex128).reshape(ref.shape), ref) < TOL_F64
+    assert rel_err(np.fromfile(tmp_path / "mom.bin", dtype=np.complex128).reshape(ref_mom.shape), ref_mom) < TOL_F64
+
+
+@pytest.mark.gpu
+def test_driver_time_split_over_two_gpus(driver, oracle, tmp_path):
+    """Two driver processes, one per GPU, each with its time slab: CUDA-IPC mapped slabs, halo slices pushed over NVLink,
+    NCCL for the flags and the time gather.  The stitched position-space buffer and the gathered momentum-space buffer
+    (on both ranks) equal the oracle's on the global lattice."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import numpy_check as npc
+    from mugiq_b200.params import momenta_up_to
+    L, nEv = (4, 4, 2, 8), 5
+    ev, U, sig = _inputs(tmp_path, L, nEv, "double")
+    mom = momenta_up_to(1)
+    (tmp_path / "mom.txt").write_text("".join(f"{p[0]} {p[1]} {p[2]}\n" for p in mom))
+    entries = [(3, 1, 1, 2), (3, 0, 1, 2), (0, 1, 1, 1), (3, 0, 1, 1)]
+    procs = []
+    for rank in range(2):
+        args = [driver, "--dim", *L, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file", tmp_path / "sig.bin",
+                "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string", "+t:1,2;-t:1,2;+x:1;-t:1",
+                "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--tsplit", 2, "--comm-size", 2,
+                "--comm-rank", rank, "--comm-id-file", tmp_path / "nccl.id", "--device", rank, "--dump-pos",
+                tmp_path / f"pos{rank}.bin", "--dump-mom", tmp_path / f"mom{rank}.bin"]
+        procs.append(subprocess.Popen([str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    ref_mom = npc.momentum_projection(ref, mom, -1, L)
+    parts = [np.fromfile(tmp_path / f"pos{r}.bin", dtype=np.complex128) for r in range(2)]
+    assert rel_err(_stitch_time_slabs(parts, ref.shape, L, 2), ref) < TOL_F64
+    for rank in range(2):
+        dm = np.fromfile(tmp_path / f"mom{rank}.bin", dtype=np.complex128).reshape(ref_mom.shape)
+        assert rel_err(dm, ref_mom) < TOL_F64
+
+
 @pytest.mark.gpu
 def test_driver_public_entry_point_and_fatal_errors(driver, tmp_path):
     """computeLoop<Float>() through the registry (no dumps), then the reference's fatal paths: position-space writing is
