@@ -89,6 +89,42 @@ def test_displace_batch_tiles(ops, oracle, L, prec):
                 assert rel_err(host(outs[i]), oracle.displace(v[i], U, d, s, L)) < tol, (d, s, i)
 
 
+@pytest.mark.parametrize("L", [(10, 6, 4, 4), (12, 5, 3, 4), (20, 7, 2, 2), (36, 3, 2, 2), (64, 2, 2, 2), (128, 2, 1, 2), (4, 16, 2, 2),
+                               (6, 9, 2, 2), (2, 3, 5, 2)])
+def test_stage_kernels_tile_geometries(ops, oracle, L):
+    """Tile selection of the bulk-TMA stage kernels over awkward extents: odd and prime Ly (one row per tile, or the whole
+    y range in one tile with the wrap inside it), half-rows longer than the tile target, Lx/2 = 1, 3, 5, 9, 32, 64."""
+    n = 3
+    v = synth.random_evecs_np(L, n, seed=45)
+    U = synth.random_gauge(L, seed=45)
+    gd = ops.gauge_upload(U, L)
+    vd = [dev(v[i]) for i in range(n)]
+    for d in range(4):
+        for s in (0, 1):
+            outs = [torch.full_like(vd[0], 7.0) for _ in range(n)]
+            ops.displace_batch(outs, vd, gd, d, s, L)
+            for i in range(n):
+                assert rel_err(host(outs[i]), oracle.displace(v[i], U, d, s, L)) < 1e-14, (d, s, i)
+    V4 = v.shape[1]
+    ref = np.zeros((16, V4), dtype=np.complex128)
+    sig = [0.4, 0.5, 0.6]
+    for i in range(n):
+        ref = oracle.contract(ref, v[i], v[(i + 1) % n], sig[i], L)
+    loop = torch.full((16, V4), 3.0, dtype=torch.complex128, device="cuda")
+    ops.contract_batch(loop, vd, [vd[(i + 1) % n] for i in range(n)], sig, L, accumulate=False)
+    assert rel_err(host(loop), ref) < TOL_F64
+    nLoop = 2
+    rng = np.random.default_rng(6)
+    pos = rng.standard_normal((nLoop, 16, V4)) + 1j * rng.standard_normal((nLoop, 16, V4))
+    out = torch.zeros(V4 * 16 * nLoop, dtype=torch.complex128, device="cuda")
+    ops.reorder_mapgamma(out, dev(pos), 16 * nLoop, nLoop, L)
+    assert np.array_equal(host(out), oracle.reorder_mapgamma(pos, nLoop, L).reshape(-1))
+    mom = momenta_up_to(2)
+    got = ops.momproj_pos(dev(pos), ops.phase_matrix_eo(mom, -1, L), nLoop, L)
+    from oracle import numpy_check as npc
+    assert rel_err(host(got), npc.momentum_projection(pos, mom, -1, L)) < TOL_F64
+
+
 @pytest.mark.parametrize("L", [(6, 2, 2, 3), (2, 2, 2, 2), (16, 4, 4, 4)])
 @pytest.mark.parametrize("same", [True, False])
 def test_contract_batch_ragged_tiles(ops, oracle, L, same):
