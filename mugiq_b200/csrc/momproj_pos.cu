@@ -58,7 +58,7 @@ __device__ __forceinline__ void dmma_m8n8k4_pos(double &c0, double &c1, const do
 // imaginary ones: one conflict-free 128-bit read per 4 DMMAs, no selects); the dataPos operand has no reuse and goes
 // straight from global memory into the B fragments, one K tile ahead of the tensor pipe.
 template <int NT>
-__global__ void __launch_bounds__(kPosWarps * 32, (NT <= 4 ? 4 : 2))
+__global__ void __launch_bounds__(kPosWarps * 32, (NT <= 4 ? 3 : 2))
 momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__ pos, const double *__restrict__ P,
                         const PosGeom pg, const int n0) {
   constexpr int kThreads = kPosWarps * 32;
@@ -126,15 +126,22 @@ momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__
     }
   };
 
+  // the dataPos operand runs kAhead tiles ahead of the tensor pipe: two for few momenta (HBM bound, registers to spare:
+  // more bytes in flight per warp), one for many (the accumulators need the registers)
+  constexpr int kAhead = NT <= 4 ? 2 : 1;
+  double2 aNN[4][2];
   ph_load(tile0);
   a_load(aT, tile0);
+  if (kAhead == 2 && tile0 + 1 < tile1) a_load(aN, tile0 + 1);
   ph_store(0);
   __syncthreads();
   for (int tile = tile0; tile < tile1; tile++) {
     const int buf = (tile - tile0) & 1;
     const bool more = tile + 1 < tile1;
-    if (more) {
-      ph_load(tile + 1);
+    if (more) ph_load(tile + 1);
+    if (kAhead == 2) {
+      if (tile + 2 < tile1) a_load(aNN, tile + 2);
+    } else if (more) {
       a_load(aN, tile + 1);
     }
     if (active) {
@@ -154,7 +161,10 @@ momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__
 #pragma unroll
     for (int ks = 0; ks < 4; ks++)
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) aT[ks][mt] = aN[ks][mt];
+      for (int mt = 0; mt < 2; mt++) {
+        aT[ks][mt] = aN[ks][mt];
+        if (kAhead == 2) aN[ks][mt] = aNN[ks][mt];
+      }
   }
   if (!active) return;
   // c-fragment: row gi -> (n, comp); columns 2j, 2j+1 -> gamma G = mt*8 + 2j + e.  Written under the mapped index.
@@ -300,9 +310,9 @@ static PosGeom make_pos_geom(const LatGeom &g, int nLoop, int N) {
     pg.blk0[c + 1] = pg.blk0[c] + (nR + kPosWarps - 1) / kPosWarps;
   }
   // split of the V3/2 run: whole tiles, at least 4 tiles per chunk, at most 16 chunks; the count that fills the 148 SMs
-  // most evenly (CTAs resident per SM: 4 for <= 16 momenta, 2 above), fewer chunks preferred (less split-K traffic)
+  // most evenly (CTAs resident per SM: 3 for <= 16 momenta, 2 above), fewer chunks preferred (less split-K traffic)
   const int ntiles = (pg.V3h + kPosKT - 1) / kPosKT;
-  const int slots = 148 * (std::min(N, 36) <= 16 ? 4 : 2);
+  const int slots = 148 * (std::min(N, 36) <= 16 ? 3 : 2);
   int best = 1;
   double best_score = -1.0;
   for (int nc = 1; nc <= 16 && nc * 4 <= std::max(ntiles, 4); nc++) {
