@@ -22,7 +22,8 @@
  * Lattice geometry and memory layouts
  *  - Sites use QUDA's even/odd (checkerboard) order: parity = (x+y+z+t)&1, x_cb = lexicographic>>1,
  *    lexicographic = x + Lx*(y + Ly*(z + Lz*t));  full-site index x_eo = x_cb + parity*volumeCB
- *    (this is `tid` of lib/mugiq_contract_kernels.cu:52).  L[0] must be even.
+ *    (this is `tid` of lib/mugiq_contract_kernels.cu:52).  L[0] must be even; every entry point that displaces
+ *    (displace*, loop_accumulate / loop_plan_create with entries) needs all four extents even, as QUDA does.
  *  - Colour-spinor fields (12 complex per site, component index = colour + 3*spin,
  *    include/util_mugiq.h:19):
  *      MUGIQ_B200_ORDER_SITE   [parity][x_cb][spin][colour]           canonical, site-major (192 B/site FP64)
@@ -208,6 +209,15 @@ int mugiq_b200_loop_plan_t_halo(const mugiq_b200_loop_plan_t *plan, int *evec_lo
 int mugiq_b200_loop_plan_accumulate(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, const void *const *evec_d,
                                     const double *sigma_h, int nvec, int accumulate, void *stream);
 int mugiq_b200_loop_plan_finalize(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, int accumulate, void *stream);
+
+/* Host-only diagnostic (no GPU needed): the fused kernel's tiling for launch group `group` of the plan these entries
+ * produce, over the time-slices [t_begin, t_end) (t_end < 0: all), checked CTA by CTA - every thread's own and neighbour
+ * site must lie in the merged intervals its CTA stages per eigenvector.  group < 0 returns the number of launch groups.
+ * out = {run (checkerboard sites per parity and CTA), warps per loop, ring stages, stage bytes, most bulk copies per
+ * stage, mean sites staged per CTA and eigenvector, sites NOT found in their stage (must be 0), malformed stage maps
+ * (must be 0)}. */
+int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int nentries, const mugiq_b200_geom_t *geom,
+                                  int t_begin, int t_end, int group, long long out[8]);
 
 /* ---- stage 3: gamma-basis / time-slice reorder -------------------------------------------------- */
 /* out[t + Lt*((15-G) + 16*iL) + Lt*nData*v3] = sign[G] * in[x_eo + V4*(G + 16*iL)].

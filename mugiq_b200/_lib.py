@@ -65,6 +65,7 @@ SYMBOLS = {
     "mugiq_b200_peer_close": (_i, [_vp]),
     "mugiq_b200_peer_free": (_i, [_vp]),
     "mugiq_b200_halo_push_t": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _i, _i, _i, _vp]),
+    "mugiq_b200_fused_tiling_check": (_i, [_pe, _i, _pg, _i, _i, _i, C.POINTER(_ll)]),
     "mugiq_b200_loop_plan_set_t_range": (_i, [_vp, _i, _i]),
     "mugiq_b200_loop_plan_t_halo": (_i, [_vp, _pi, _pi, _pi]),
     "mugiq_b200_loop_plan_accumulate": (_i, [_vp, _vp, _pvp, _pd, _i, _i, _vp]),

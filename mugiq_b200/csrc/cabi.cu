@@ -32,6 +32,17 @@ int check_geom(const mugiq_b200_geom_t *geom, const char *who) {
   return MUGIQ_B200_OK;
 }
 
+// Displacements need every extent even: the neighbour of a site is looked up as (checkerboard index, opposite parity),
+// which breaks across the periodic wrap of an odd extent (the wrapped site keeps its parity).  QUDA, and with it the
+// reference, only runs on even local extents.  Contraction, reorder and projection are site-local and take any Ly, Lz, Lt.
+int check_geom_even(const mugiq_b200_geom_t *geom, const char *who) {
+  for (int i = 1; i < 4; i++)
+    if (geom->L[i] & 1)
+      return set_error(MUGIQ_B200_EINVAL, "%s: L[%d] = %d must be even for displacements (even/odd neighbour lookup)", who, i,
+                       geom->L[i]);
+  return MUGIQ_B200_OK;
+}
+
 static int check_dir_sign(int dir, int sign, const char *who) {
   // Displace::setupDisplacement rejects anything else (lib/displace.cpp:214-222)
   if (dir < 0 || dir > 3) return set_error(MUGIQ_B200_EINVAL, "%s: invalid displacement direction %d", who, dir);
@@ -221,6 +232,7 @@ int mugiq_b200_displace(void *dst_d, const void *src_d, const void *gauge_d, int
   const char *who = "mugiq_b200_displace";
   int rc = check_geom(geom, who);
   if (rc) return rc;
+  if ((rc = check_geom_even(geom, who))) return rc;
   REQUIRE_PTR(dst_d, who);
   REQUIRE_PTR(src_d, who);
   REQUIRE_PTR(gauge_d, who);
@@ -235,6 +247,7 @@ int mugiq_b200_displace_batch(void *const *dst_d, const void *const *src_d, int 
   const char *who = "mugiq_b200_displace_batch";
   int rc = check_geom(geom, who);
   if (rc) return rc;
+  if ((rc = check_geom_even(geom, who))) return rc;
   REQUIRE_PTR(dst_d, who);
   REQUIRE_PTR(src_d, who);
   REQUIRE_PTR(gauge_d, who);
@@ -275,6 +288,7 @@ int mugiq_b200_displace_native(void *const *dst_d, const void *const *src_d, int
   const char *who = "mugiq_b200_displace_native";
   int rc = check_geom(geom, who);
   if (rc) return rc;
+  if ((rc = check_geom_even(geom, who))) return rc;
   if ((rc = check_native_order(order, who))) return rc;
   REQUIRE_PTR(dst_d, who);
   REQUIRE_PTR(src_d, who);
@@ -309,6 +323,7 @@ int mugiq_b200_loop_accumulate(void *dataPos_d, const void *const *evec_d, const
   REQUIRE_PTR(sigma_h, who);
   if (nvec < 1) return set_error(MUGIQ_B200_EINVAL, "%s: nvec = %d must be positive", who, nvec);
   if ((rc = check_entries(entries, nentries, who))) return rc;
+  if (nentries > 0 && (rc = check_geom_even(geom, who))) return rc;
   if (nentries > 0) REQUIRE_PTR(gauge_d, who);
   for (int i = 0; i < nvec; i++)
     if (!evec_d[i]) return set_error(MUGIQ_B200_EINVAL, "%s: eigenvector %d is NULL", who, i);

@@ -47,7 +47,8 @@ inline LatGeom make_geom(const int L[4]) {
   return g;
 }
 
-int check_geom(const mugiq_b200_geom_t *geom, const char *who);  // cabi.cu
+int check_geom(const mugiq_b200_geom_t *geom, const char *who);       // cabi.cu
+int check_geom_even(const mugiq_b200_geom_t *geom, const char *who);  // cabi.cu: every extent even (displacements)
 
 // QUDA getCoords(x, cb_index, X, parity) for a full (two-parity) field.
 __host__ __device__ inline void get_coords(int x[4], int cb, int parity, const LatGeom &g) {

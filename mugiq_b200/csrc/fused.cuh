@@ -7,8 +7,7 @@ namespace mugiq_b200 {
 
 constexpr int kFusedMaxVec = 256;    // eigenvectors per launch (pointer + 1/sigma table travels as a kernel parameter)
 constexpr int kFusedMaxLoops = 4;    // displaced loops per launch group (the ultra-local loop rides along for free)
-constexpr int kFusedMaxRows = 4;     // lattice rows (fixed y,z,t; all x) per CTA tile
-constexpr int kFusedMaxSlots = kFusedMaxRows * (kFusedMaxLoops + 1);  // staged rows per eigenvector: own + shifted
+constexpr int kFusedMaxIv = 64;      // merged intervals (= bulk copies) of one eigenvector stage
 // 8 warps = 2 per SM sub-partition: each sub-partition owns 16384 registers, so 2 warps may use up to 255 registers
 // per thread (a third warp would cap the kernel at 168 and spill the 4x4 spin matrix + link + operands)
 constexpr int kFusedComputeWarps = 8;
@@ -29,13 +28,12 @@ struct FusedGroup {
   int nloops;
 };
 
-// Tile geometry chosen on the host (same for every CTA): NR = TY*TZ*TT rows per tile.
+// Tile geometry chosen on the host (same for every CTA): a CTA works on `run` consecutive checkerboard sites of both
+// parities; what a stage holds is worked out per CTA (fused_kernel.cu, StageMap).
 struct FusedTiling {
-  int TY, TZ, TT, NR;
-  int nTy, nTz, nTt;     // tiles per dimension
-  int units;             // warps per loop: ceil(sitesPerTile / 32)
-  int nslots;            // staged rows per eigenvector (own + de-duplicated shifted rows), <= kFusedMaxSlots
-  int stage_bytes;       // nslots * 2 half-rows of Lx/2 sites, rounded up to 128 B
+  int run;          // consecutive checkerboard sites per parity and CTA (multiple of 32)
+  int units;        // warps per loop of the group: 2 * run / 32
+  int stage_bytes;  // largest stage over the CTAs of the launch (merged intervals), rounded up to 128 B
   int nstages;
 };
 
@@ -48,10 +46,13 @@ struct FusedVecTable {
 // maximum number of displaced loops per group for this lattice / precision (warp and shared-memory budget)
 int fused_max_loops_per_group(const LatGeom &g, int precision);
 // Launches one group (0..kFusedMaxLoops displaced loops, plus the ultra-local loop if ul_off >= 0) for up to kFusedMaxVec
-// eigenvectors over the sites of the time-slices [t_begin, t_end) (rounded outwards to whole tiles; the whole lattice
-// for 0, Lt): a rank of a lattice-T split computes its interior only and merely READS the halo slices.
+// eigenvectors over the sites of the time-slices [t_begin, t_end) (the whole lattice for 0, Lt): a rank of a lattice-T split computes its interior only and merely READS the halo slices.
 int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,
                        const LatGeom &g, int precision, cudaStream_t stream, int t_begin = 0, int t_end = -1);
+
+// host-only self-check of the tiling of one launch group (fused_kernel.cu); out = {run, units, nstages, stage_bytes,
+// max copies per stage, mean sites staged per CTA, sites not found in their stage, malformed stage maps}
+int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, long long out[8]);
 
 // ---- gauge-only helpers (wilson.cu) ---------------------------------------------------------------------
 // Wout(x) = Win(x) * U_dir(x + shift*dir)       (extends a plus-direction Wilson line by one link)

@@ -17,13 +17,18 @@
 //    HBM traffic per (eigvec, site).  Everything else is arranged so that the FP64 pipe is the only busy unit:
 //    on this chip every other instruction takes FP64 issue slots (one IMAD per DFMA halves the DFMA rate,
 //    tools/microbench.cu), so the loop body is ~390 FP64 + ~175 other instructions per eigenvector.
-//  * CTA tile = NR (<= 4) lattice rows (all x at fixed y,z,t), preferably consecutive in y: in the even/odd
-//    site-major layout a row is two contiguous half-rows (one per parity) of Lx/2 sites x 192 B and consecutive-y
-//    rows are contiguous, so the tile and its shifted copies are fetched with a handful of multi-KB bulk-TMA
-//    copies (cp.async.bulk + mbarrier complete_tx; small copies cost ~100-500 cycles each, tools/tma_bench.cu).
-//    Per eigenvector a stage holds the tile's own rows plus the rows shifted by every displacement of the group,
-//    de-duplicated; x-displacements stay inside the row (periodic wrap).  Layout in shared memory is dense:
-//    [parity][slot][Lx/2 sites][12 complex].
+//  * CTA tile = a RUN of 32*k consecutive checkerboard sites [c0, c0 + run) of BOTH parities (k = 1 with 3 or 4
+//    displaced loops in the group).  In the even/odd site-major layout a lattice row (all x at fixed y,z,t) is two
+//    contiguous half-rows (one per parity) of Lx/2 sites x 192 B and rows consecutive in y are contiguous, so for
+//    Lx/2 = 8, 16, 32 a run is 4, 2, 1 whole rows; for Lx/2 = 12, 24 (24^3x48, 48^3x96) it is a fractional number of
+//    rows and still fills every lane of every warp (whole-row tiles left 8 of 32 lanes idle there).  What a stage
+//    holds per eigenvector is a union of INTERVALS of checkerboard-index space: the run itself, and for every loop of
+//    the group the image of each row piece of the run under the shift (y, z, t shifts move a piece to another row of
+//    the opposite or same parity; an x shift of length k needs the piece widened by ceil(k/2) sites, wrapped inside
+//    its row).  Overlapping and adjoining intervals are merged, so every interval is ONE bulk-TMA copy
+//    (cp.async.bulk + mbarrier complete_tx; small copies cost ~100-500 cycles each, tools/tma_bench.cu) and shared
+//    sites (the +y image of a run overlaps the run) are fetched once.  Layout in shared memory is dense:
+//    [interval][site][12 complex].
 //  * 8 warps (2 per SM sub-partition -> 255 registers per thread, no spills): warp = (loop, parity-half of the
 //    tile), thread = (site, loop) and owns the 4x4 complex spin matrix M (32 doubles), the 3x3 link W (18) and its
 //    share of the Hermitian ultra-local matrix for the whole batch.  Every warp issues its share of the TMA copies
@@ -34,7 +39,12 @@
 //    rotated by k = (site_index/2) mod 4, i.e. it keeps spin (b+k) mod 4 in register slot b.  The 8 lanes of a
 //    quarter-warp then touch 8 distinct bank groups (conflict-free 128-bit reads); the rotation only relabels
 //    M[be][al] and is undone once in the epilogue.
+#include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "fused.cuh"
 
@@ -46,17 +56,19 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 
-// ---- staged-row ("slot") table of a tile: shared by host (sizing) and device -------------------------------
-constexpr int kMaxCopies = 2 * kFusedMaxSlots;
-struct SlotTable {
-  int row[kFusedMaxSlots];                 // lexicographic row index y + Ly*(z + Lz*t) of each slot
-  int nbr[kFusedMaxLoops][kFusedMaxRows];  // slot holding the shifted row of own row i for loop j
-  int nslots;
-  // bulk copies of one stage: runs of slots whose rows are consecutive in memory, per parity
-  int ncopies;
-  int cp_soff[kMaxCopies];    // byte offset inside the stage
-  int cp_goff16[kMaxCopies];  // offset inside the eigenvector, in units of 16 B
-  int cp_bytes[kMaxCopies];
+// ---- stage map of a tile: the merged intervals of checkerboard-index space one eigenvector stage holds ------------
+// shared by host (sizing) and device (thread 0 of every CTA builds its own)
+constexpr int kMaxIv = kFusedMaxIv;
+struct StageMap {
+  int n;         // merged intervals = bulk copies per stage
+  int sites;     // sites per stage
+  int overflow;  // more than kMaxIv intervals (the host checks this before launching)
+  int par[kMaxIv], lo[kMaxIv], hi[kMaxIv];  // interval [lo, hi) of checkerboard indices of parity par, sorted by (par, lo)
+  int soff[kMaxIv];                          // first site of the interval inside the stage
+  // the bulk copies, precomputed for the issuing lanes
+  int cp_soff[kMaxIv];    // byte offset inside the stage
+  int cp_goff16[kMaxIv];  // offset inside the eigenvector, in units of 16 B
+  int cp_bytes[kMaxIv];
 };
 
 __host__ __device__ inline int wrap(int a, int n) {
@@ -64,53 +76,119 @@ __host__ __device__ inline int wrap(int a, int n) {
   return a < 0 ? a + n : a;
 }
 
-__host__ __device__ inline void build_slots(SlotTable &st, const FusedGroup &grp, const FusedTiling &tl, const LatGeom &g,
-                                            int site_bytes, int y0, int z0, int t0) {
-  int nslots = tl.NR;
-  for (int i = 0; i < tl.NR; i++) {
-    const int a = i % tl.TY, b = (i / tl.TY) % tl.TZ, c = i / (tl.TY * tl.TZ);
-    st.row[i] = (y0 + a) + g.L[1] * ((z0 + b) + g.L[2] * (t0 + c));
+// insert [lo, hi) of parity par into the sorted list of disjoint intervals, merging what overlaps or adjoins
+__host__ __device__ inline void iv_insert(StageMap &m, int par, int lo, int hi) {
+  if (lo >= hi) return;
+  int i = 0;
+  while (i < m.n && (m.par[i] < par || (m.par[i] == par && m.hi[i] < lo))) i++;
+  if (i < m.n && m.par[i] == par && m.lo[i] <= hi) {  // touches interval i: grow it, swallow the followers it reaches
+    if (lo < m.lo[i]) m.lo[i] = lo;
+    if (hi > m.hi[i]) m.hi[i] = hi;
+    int k = i + 1;
+    while (k < m.n && m.par[k] == par && m.lo[k] <= m.hi[i]) {
+      if (m.hi[k] > m.hi[i]) m.hi[i] = m.hi[k];
+      k++;
+    }
+    if (k > i + 1) {
+      for (int d = i + 1, s = k; s < m.n; d++, s++) {
+        m.par[d] = m.par[s];
+        m.lo[d] = m.lo[s];
+        m.hi[d] = m.hi[s];
+      }
+      m.n -= k - (i + 1);
+    }
+    return;
   }
+  if (m.n == kMaxIv) {
+    m.overflow = 1;
+    return;
+  }
+  for (int d = m.n; d > i; d--) {
+    m.par[d] = m.par[d - 1];
+    m.lo[d] = m.lo[d - 1];
+    m.hi[d] = m.hi[d - 1];
+  }
+  m.par[i] = par;
+  m.lo[i] = lo;
+  m.hi[i] = hi;
+  m.n++;
+}
+
+// Stage of the run [c0, c1) (both parities) for the loops of grp: the run itself plus, per loop, the image of every row
+// piece of the run.  A y/z/t shift maps the piece [a, b) of row r to the same positions of the shifted row; an x shift
+// of length k keeps the row and moves the half-row index by at most ceil(k/2) (periodic inside the row).  Both
+// parities are staged for every image: a site's neighbour has parity p ^ (k & 1) and both own parities are in the tile.
+__host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &grp, const LatGeom &g, int site_bytes, int c0,
+                                                int c1) {
+  m.n = 0;
+  m.overflow = 0;
+  const int Lh = g.Lh;
+  for (int p = 0; p < 2; p++) iv_insert(m, p, c0, c1);
   for (int j = 0; j < grp.nloops; j++) {
     const FusedLoop &lp = grp.loop[j];
-    for (int i = 0; i < tl.NR; i++) {
-      if (lp.dir == 0) {  // x-displacement: the neighbour lives in the same row
-        st.nbr[j][i] = i;
-        continue;
+    const int sh = lp.sign * lp.len;
+    for (int c = c0; c < c1;) {
+      const int row = c / Lh, a = c - row * Lh;
+      int b = a + (c1 - c);
+      if (b > Lh) b = Lh;
+      const int base = row * Lh;
+      if (lp.dir == 0) {
+        const int h = (lp.len + 1) >> 1;
+        int lo = a - h, hi = b + h;
+        if (hi - lo >= Lh) {
+          lo = 0;
+          hi = Lh;
+        }
+        for (int p = 0; p < 2; p++) {
+          if (lo < 0) iv_insert(m, p, base + lo + Lh, base + Lh);
+          if (hi > Lh) iv_insert(m, p, base, base + hi - Lh);
+          iv_insert(m, p, base + (lo < 0 ? 0 : lo), base + (hi > Lh ? Lh : hi));
+        }
+      } else {
+        int y = row % g.L[1], z = (row / g.L[1]) % g.L[2], t = row / (g.L[1] * g.L[2]);
+        if (lp.dir == 1) y = wrap(y + sh, g.L[1]);
+        if (lp.dir == 2) z = wrap(z + sh, g.L[2]);
+        if (lp.dir == 3) t = wrap(t + sh, g.L[3]);
+        const int nb = (y + g.L[1] * (z + g.L[2] * t)) * Lh;
+        for (int p = 0; p < 2; p++) iv_insert(m, p, nb + a, nb + b);
       }
-      const int a = i % tl.TY, b = (i / tl.TY) % tl.TZ, c = i / (tl.TY * tl.TZ);
-      int y = y0 + a, z = z0 + b, t = t0 + c;
-      const int sh = lp.sign * lp.len;
-      if (lp.dir == 1) y = wrap(y + sh, g.L[1]);
-      if (lp.dir == 2) z = wrap(z + sh, g.L[2]);
-      if (lp.dir == 3) t = wrap(t + sh, g.L[3]);
-      const int r = y + g.L[1] * (z + g.L[2] * t);
-      int found = -1;
-      for (int k = 0; k < nslots; k++)
-        if (st.row[k] == r) found = k;
-      if (found < 0) {
-        found = nslots++;
-        st.row[found] = r;
-      }
-      st.nbr[j][i] = found;
+      c += b - a;
     }
   }
-  st.nslots = nslots;
-  // merge slots with consecutive rows into one copy per parity
-  const int hrb = g.Lh * site_bytes;
-  int nc = 0;
-  for (int k = 0; k < nslots;) {
-    int len = 1;
-    while (k + len < nslots && st.row[k + len] == st.row[k] + len) len++;
-    for (int p = 0; p < 2; p++) {
-      st.cp_soff[nc] = (p * nslots + k) * hrb;
-      st.cp_goff16[nc] = (int)((((long long)p * g.volumeCB + (long long)st.row[k] * g.Lh) * site_bytes) >> 4);
-      st.cp_bytes[nc] = len * hrb;
-      nc++;
-    }
-    k += len;
+  int off = 0;
+  for (int i = 0; i < m.n; i++) {
+    m.soff[i] = off;
+    m.cp_soff[i] = off * site_bytes;
+    m.cp_goff16[i] = (int)((((long long)m.par[i] * g.volumeCB + m.lo[i]) * site_bytes) >> 4);
+    m.cp_bytes[i] = (m.hi[i] - m.lo[i]) * site_bytes;
+    off += m.hi[i] - m.lo[i];
   }
-  st.ncopies = nc;
+  m.sites = off;
+}
+
+// position (in sites) of checkerboard site cb of parity par inside the stage; -1 if the stage does not hold it
+__host__ __device__ inline int stage_site(const StageMap &m, int par, int cb) {
+  for (int i = 0; i < m.n; i++)
+    if (m.par[i] == par && m.lo[i] <= cb && cb < m.hi[i]) return m.soff[i] + cb - m.lo[i];
+  return -1;
+}
+
+// checkerboard index of the site x + sign*len*dir a loop reads for the own site (parity p, checkerboard index cb);
+// its parity is p ^ (len & 1).  Neighbour selection of lib/mugiq_displace_kernels.cu:116-151 for a hop of `len` links.
+__host__ __device__ inline int neighbour_cb(const LatGeom &g, const FusedLoop &lp, int p, int cb) {
+  const int Lh = g.Lh;
+  const int row = cb / Lh, sx = cb - row * Lh;
+  const int ya = row % g.L[1], za = (row / g.L[1]) % g.L[2], ta = row / (g.L[1] * g.L[2]);
+  const int sh = lp.sign * lp.len;
+  if (lp.dir == 0) {
+    const int x = 2 * sx + ((ya + za + ta + p) & 1);
+    return row * Lh + (wrap(x + sh, g.L[0]) >> 1);
+  }
+  int yn = ya, zn = za, tn = ta;
+  if (lp.dir == 1) yn = wrap(ya + sh, g.L[1]);
+  if (lp.dir == 2) zn = wrap(za + sh, g.L[2]);
+  if (lp.dir == 3) tn = wrap(ta + sh, g.L[3]);
+  return (yn + g.L[1] * (zn + g.L[2] * tn)) * Lh + sx;
 }
 
 template <typename F> struct FusedArgs {
@@ -121,10 +199,11 @@ template <typename F> struct FusedArgs {
   F *dataPos;
   long long ul_off;    // complex offset of the ultra-local loop's block in dataPos, < 0: not in this launch
   int accumulate;
-  int tt0;             // first tile in t of this launch (time-slice range of a lattice-T split; 0 = whole lattice)
+  int c_begin, c_end;  // checkerboard-index range [c_begin, c_end) of both parities this launch computes: the time-slices
+                       // [t_begin, t_end) of a lattice-T split slab, or the whole lattice
 };
 
-constexpr int kSmemHeader = 2048;  // barriers + slot table
+constexpr int kSmemHeader = 3072;  // barriers + stage map
 
 template <typename F> __device__ __forceinline__ Cplx<F> lds_c(const char *p) {
   using V = typename vec2_of<F>::type;
@@ -169,7 +248,7 @@ template <typename F, bool kRow> __device__ __forceinline__ void unrotate_rt(Cpl
 template <typename F> struct ThreadCtx {
   const char *stages;
   uint64_t *full, *empty;
-  const SlotTable *st;
+  const StageMap *st;
   int S, stage_bytes, nvec, ahead, nActive, warp, lane;
   int own_sp[4], nbr_sp[4];  // byte offsets (inside a stage) of the 4 rotated spin blocks of v(x) and v(x+d)
 };
@@ -226,7 +305,7 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
   // chip are paid in FP64 issue slots; spread over the warps in turn it is ~15 per warp and eigenvector instead of ~65
   // when every warp issued its own share every time.
   uint32_t total_tx = 0;
-  for (int i = 0; i < c.st->ncopies; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
+  for (int i = 0; i < c.st->n; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
   const int lead = c.lane == 0;
   const uint32_t stages_u32 = smem_u32(c.stages);
   const uint32_t full_u32 = smem_u32(c.full), empty_u32 = smem_u32(c.empty);
@@ -242,7 +321,7 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
       if (wait) mbar_wait_u32(p_empty, p_par);
       const char *ev = static_cast<const char *>(A.vt.evec[m]);
       mbar_expect_tx_if(p_full, total_tx, lead);
-      for (int i = c.lane; i < c.st->ncopies; i += 32)
+      for (int i = c.lane; i < c.st->n; i += 32)
         tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4), (uint32_t)c.st->cp_bytes[i],
                         p_full, 1);
       turn = c.nActive;
@@ -354,7 +433,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);        // [nstages]
   uint64_t *empty = reinterpret_cast<uint64_t *>(smem + 64);  // [nstages]
-  SlotTable &st = *reinterpret_cast<SlotTable *>(smem + 128);
+  StageMap &st = *reinterpret_cast<StageMap *>(smem + 128);
   const LatGeom &g = A.g;
   const FusedTiling &tl = A.tl;
   F *xch = reinterpret_cast<F *>(smem + kSmemHeader);  // [units*32][16] ultra-local entries, true spin labels
@@ -365,15 +444,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   constexpr int nrole = ND > 0 ? ND : 1;  // a launch without displaced loops runs one pure ultra-local role
   const int nActive = nrole * tl.units;   // compute warps in use
   constexpr int kSite = 24 * (int)sizeof(F);
-  const int Lh = g.Lh;
 
-  const int bid = blockIdx.x;
-  const int y0 = (bid % tl.nTy) * tl.TY;
-  const int z0 = ((bid / tl.nTy) % tl.nTz) * tl.TZ;
-  const int t0 = (bid / (tl.nTy * tl.nTz) + A.tt0) * tl.TT;
+  // this CTA's run of checkerboard sites (both parities)
+  const int c0 = A.c_begin + (int)blockIdx.x * tl.run;
+  const int c1 = min(c0 + tl.run, A.c_end);
 
   if (threadIdx.x == 0) {
-    build_slots(st, A.grp, tl, g, kSite, y0, z0, t0);
+    build_stage_map(st, A.grp, g, kSite, c0, c1);
     for (int s = 0; s < tl.nstages; s++) {
       mbar_init(&full[s], 1);        // one arrive.expect_tx by the warp whose turn it is
       mbar_init(&empty[s], nActive);
@@ -383,21 +460,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   __syncthreads();
 
   const bool active = warp < nActive;
-  // ---- role of this thread: displaced loop j (if any) on site q of parity p ------------------------------------
+  // ---- role of this thread: displaced loop j (if any) on site c0 + q of parity p -------------------------------
   const int j = active ? warp / tl.units : 0, u = active ? warp % tl.units : 0;
   const int upp = tl.units >> 1;  // warps per parity
-  const int nsite = tl.NR * Lh;   // sites of one parity in the tile
   const int p = u / upp;
   int q = (u % upp) * 32 + lane;
-  const bool valid = active && q < nsite;
-  if (!valid) q = 0;                      // park on a real site; nothing is stored
-  const int i = q / Lh, sx = q - i * Lh;  // own row, position in the half-row
-  const int ya = y0 + i % tl.TY, za = z0 + (i / tl.TY) % tl.TZ, ta = t0 + i / (tl.TY * tl.TZ);
-  const int x = 2 * sx + ((ya + za + ta + p) & 1);
-  const size_t x_eo = (size_t)p * g.volumeCB + (size_t)st.row[i] * Lh + sx;
-  const int hrb = Lh * kSite;
-  const bool ul_rot = has_ul && ND == 4;              // see UL_ROT
-  const int k_own = (((q >> 1) & 3) + (ul_rot ? j : 0)) & 3;  // spin-label rotation of v(x): bank rotation + role rotation
+  const bool valid = active && c0 + q < c1;
+  if (!valid) q = 0;  // park on a real site; nothing is stored
+  const int cb = c0 + q;
+  const size_t x_eo = (size_t)p * g.volumeCB + (size_t)cb;
+  const bool ul_rot = has_ul && ND == 4;  // see UL_ROT
+  const int s_own = max(stage_site(st, p, cb), 0);
+  const int k_own = (((s_own >> 1) & 3) + (ul_rot ? j : 0)) & 3;  // spin-label rotation of v(x): bank rotation + role rotation
   int k_nbr = 0;
 
   ThreadCtx<F> c;
@@ -413,21 +487,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   c.warp = warp;
   c.lane = lane;
   {
-    const int off = p * st.nslots * hrb + q * kSite;
+    const int off = s_own * kSite;
 #pragma unroll
     for (int b = 0; b < 4; b++) c.own_sp[b] = off + ((b + k_own) & 3) * (kSite / 4);
   }
   const FusedLoop lp = A.grp.loop[ND > 0 ? j : 0];
   if (ND > 0) {
-    const int pn = (p + lp.len) & 1;
-    int slot = i, sn = sx;
-    if (lp.dir == 0)
-      sn = wrap(x + lp.sign * lp.len, g.L[0]) >> 1;
-    else
-      slot = st.nbr[j][i];
-    const int qn = slot * Lh + sn;
-    k_nbr = (qn >> 1) & 3;
-    const int off = pn * st.nslots * hrb + qn * kSite;
+    // neighbour x + sign*len*dir and its place in the stage
+    const int s_nbr = max(stage_site(st, (p + lp.len) & 1, neighbour_cb(g, lp, p, cb)), 0);
+    k_nbr = (s_nbr >> 1) & 3;
+    const int off = s_nbr * kSite;
 #pragma unroll
     for (int b = 0; b < 4; b++) c.nbr_sp[b] = off + ((b + k_nbr) & 3) * (kSite / 4);
   } else {
@@ -537,49 +606,118 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
 }
 
 // ---- host side: tiling and launch ----------------------------------------------------------------------------
-static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int smem_limit) {
-  // consecutive-y rows first: they are contiguous in memory, so own rows and shifted rows arrive as few large copies
-  static const int cand[][3] = {{4, 1, 1}, {2, 2, 1}, {2, 1, 2}, {1, 2, 2}, {1, 4, 1}, {1, 1, 4},
-                                {2, 1, 1}, {1, 2, 1}, {1, 1, 2}, {1, 1, 1}};
-  const int site = 24 * (int)prec_bytes(precision);
-  const int nrole = grp.nloops > 0 ? grp.nloops : 1;
-  for (const auto &c : cand) {
-    if (g.L[1] % c[0] || g.L[2] % c[1] || g.L[3] % c[2]) continue;
-    tl.TY = c[0];
-    tl.TZ = c[1];
-    tl.TT = c[2];
-    tl.NR = c[0] * c[1] * c[2];
-    tl.nTy = g.L[1] / c[0];
-    tl.nTz = g.L[2] / c[1];
-    tl.nTt = g.L[3] / c[2];
-    tl.units = 2 * ((tl.NR * g.Lh + 31) / 32);
-    if (tl.units * nrole > kFusedComputeWarps) continue;
-    SlotTable st;
-    build_slots(st, grp, tl, g, site, 0, 0, 0);
-    tl.nslots = st.nslots;
-    tl.stage_bytes = (tl.nslots * 2 * g.Lh * site + 127) / 128 * 128;
-    tl.nstages = (smem_limit - kSmemHeader - tl.units * 32 * 16 * (int)prec_bytes(precision)) / tl.stage_bytes;
-    if (tl.nstages > 8) tl.nstages = 8;
-    if (const char *e = getenv("MUGIQ_B200_FUSED_STAGES")) {
-      const int want = atoi(e);
-      if (want >= 2 && want < tl.nstages) tl.nstages = want;
-    }
-    if (tl.nstages >= 2) return true;
+static int smem_limit_bytes() {
+  // the opt-in limit is a per-device attribute: one cached value per device ordinal (one process may drive several GPUs)
+  static int limit[64];
+  static bool known[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 227 * 1024;
+  if (!known[dev]) {
+    int v = 0;
+    limit[dev] = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess ? v : 227 * 1024;
+    known[dev] = true;
   }
-  return false;
+  return limit[dev];
 }
 
-static int smem_limit_bytes() {
-  static int limit = -1;
-  if (limit < 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess)
-      limit = v;
-    else
-      limit = 227 * 1024;
+// Largest stage (in sites) over the CTAs of a launch, exact: the merged intervals of every run are evaluated once per
+// (lattice, group, run, range) and remembered - 10^4 runs of a few dozen interval insertions each.
+static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int c_begin, int c_end, bool *overflow) {
+  static std::mutex mu;
+  static std::map<std::vector<int>, std::pair<int, bool>> cache;
+  std::vector<int> key = {g.L[0], g.L[1], g.L[2], g.L[3], run, c_begin, c_end, grp.nloops};
+  for (int j = 0; j < grp.nloops; j++) {
+    key.push_back(grp.loop[j].dir);
+    key.push_back(grp.loop[j].sign);
+    key.push_back(grp.loop[j].len);
   }
-  return limit;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    int best = 0;
+    bool ovf = false;
+    StageMap m;
+    for (int c0 = c_begin; c0 < c_end; c0 += run) {
+      build_stage_map(m, grp, g, 1, c0, std::min(c0 + run, c_end));
+      best = std::max(best, m.sites);
+      ovf = ovf || m.overflow;
+    }
+    it = cache.emplace(key, std::make_pair(best, ovf)).first;
+  }
+  *overflow = it->second.second;
+  return it->second.first;
+}
+
+// Run length: 8 warps = (loops of the group) x (warps per loop), a warp = 32 consecutive sites of one parity, so a group
+// of 3 or 4 displaced loops gets runs of 32 sites per parity, 2 loops 64, 1 loop or the ultra-local loop alone 128;
+// shorter if the shared-memory ring would otherwise have fewer than 3 stages.
+static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int smem_limit, int c_begin,
+                          int c_end) {
+  const int site = 24 * (int)prec_bytes(precision);
+  const int nrole = grp.nloops > 0 ? grp.nloops : 1;
+  int max_stages = 8;
+  if (const char *e = getenv("MUGIQ_B200_FUSED_STAGES")) {
+    const int want = atoi(e);
+    if (want >= 2 && want < max_stages) max_stages = want;
+  }
+  FusedTiling best;
+  best.nstages = 0;
+  for (int units = (kFusedComputeWarps / nrole) & ~1; units >= 2; units -= 2) {
+    FusedTiling t;
+    t.units = units;
+    t.run = 16 * units;
+    bool overflow = false;
+    const int sites = max_stage_sites(grp, g, t.run, c_begin, c_end, &overflow);
+    if (overflow) continue;
+    t.stage_bytes = (sites * site + 127) / 128 * 128;
+    t.nstages = std::min(max_stages, (smem_limit - kSmemHeader - t.units * 32 * 16 * (int)prec_bytes(precision)) / t.stage_bytes);
+    if (t.nstages > best.nstages) best = t;
+    if (best.nstages >= std::min(3, max_stages)) break;
+  }
+  if (best.nstages < 2) return false;
+  tl = best;
+  return true;
+}
+
+// Host-only self-check of the tiling (no GPU needed; exported as mugiq_b200_fused_tiling_check for the CPU tests): for
+// every CTA of a launch, the stage map must be sorted, disjoint and within the sized stage, and every thread's own and
+// neighbour site must lie in it.
+int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, long long out[8]) {
+  FusedTiling tl;
+  const int V3h = g.V3 / 2, c_begin = t_begin * V3h, c_end = t_end * V3h;
+  if (!choose_tiling(tl, grp, g, precision, 227 * 1024, c_begin, c_end))
+    return set_error(MUGIQ_B200_EINVAL, "fused_tiling_check: no tiling fits");
+  const int site = 24 * (int)prec_bytes(precision);
+  long long misses = 0, bad_maps = 0, stage_sites = 0, ctas = 0;
+  int max_copies = 0;
+  StageMap m;
+  for (int c0 = c_begin; c0 < c_end; c0 += tl.run) {
+    const int c1 = std::min(c0 + tl.run, c_end);
+    build_stage_map(m, grp, g, site, c0, c1);
+    ctas++;
+    stage_sites += m.sites;
+    max_copies = std::max(max_copies, m.n);
+    if (m.overflow || m.sites * site > tl.stage_bytes) bad_maps++;
+    for (int i = 0; i + 1 < m.n; i++)
+      if (m.par[i] > m.par[i + 1] || (m.par[i] == m.par[i + 1] && m.hi[i] >= m.lo[i + 1])) bad_maps++;
+    for (int i = 0; i < m.n; i++)
+      if (m.lo[i] < 0 || m.hi[i] > g.volumeCB || m.lo[i] >= m.hi[i] || (m.cp_bytes[i] & 15) || (m.cp_soff[i] & 15)) bad_maps++;
+    for (int p = 0; p < 2; p++)
+      for (int cb = c0; cb < c1; cb++) {
+        if (stage_site(m, p, cb) < 0) misses++;
+        for (int j = 0; j < grp.nloops; j++)
+          if (stage_site(m, (p + grp.loop[j].len) & 1, neighbour_cb(g, grp.loop[j], p, cb)) < 0) misses++;
+      }
+  }
+  out[0] = tl.run;
+  out[1] = tl.units;
+  out[2] = tl.nstages;
+  out[3] = tl.stage_bytes;
+  out[4] = max_copies;
+  out[5] = ctas ? stage_sites / ctas : 0;  // mean sites staged per CTA and eigenvector
+  out[6] = misses;
+  out[7] = bad_maps;
+  return MUGIQ_B200_OK;
 }
 
 int fused_max_loops_per_group(const LatGeom &g, int precision) {
@@ -595,17 +733,20 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
       grp.loop[j].out_off = 0;
     }
     FusedTiling tl;
-    if (choose_tiling(tl, grp, g, precision, smem_limit_bytes())) return nl;
+    if (choose_tiling(tl, grp, g, precision, smem_limit_bytes(), 0, g.volumeCB)) return nl;
   }
   return -1;
 }
 
 template <typename F, int ND> static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the shared-memory opt-in is a per-device function attribute
+  static bool attr_set[64];
+  int dev = 0;
+  MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           smem_limit_bytes()));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   loop_fused_kernel<F, ND><<<grid, kFusedThreads, smem, stream>>>(args);
   MUGIQ_LAUNCH_CHECK();
@@ -622,14 +763,15 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   args.ul_off = ul_off;
   args.dataPos = static_cast<F *>(dataPos_d);
   args.accumulate = accumulate;
-  if (!choose_tiling(args.tl, grp, g, precision, smem_limit_bytes()))
+  // time-slice range -> range of checkerboard indices (a time-slice is V3/2 consecutive sites of each parity)
+  const int V3h = g.V3 / 2;
+  args.c_begin = t_begin * V3h;
+  args.c_end = t_end * V3h;
+  if (!choose_tiling(args.tl, grp, g, precision, smem_limit_bytes(), args.c_begin, args.c_end))
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
-  // time-slice range -> whole tiles in t
-  const int tt0 = t_begin / args.tl.TT, tt1 = (t_end + args.tl.TT - 1) / args.tl.TT;
-  args.tt0 = tt0;
-  const int grid = args.tl.nTy * args.tl.nTz * (tt1 - tt0);
-  const double frac = (double)(tt1 - tt0) / (double)args.tl.nTt;  // share of the lattice this launch computes
+  const int grid = (args.c_end - args.c_begin + args.tl.run - 1) / args.tl.run;
+  const double frac = (double)(t_end - t_begin) / (double)g.L[3];  // share of the lattice this launch computes
   const size_t smem =
       kSmemHeader + (size_t)args.tl.units * 32 * 16 * sizeof(F) + (size_t)args.tl.nstages * args.tl.stage_bytes;
   // algorithmic (compulsory) bytes: every eigenvector site once, every link once, the accumulators once

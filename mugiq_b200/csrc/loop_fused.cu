@@ -143,6 +143,50 @@ static void plan_layout(LoopPlan &pl, const LatGeom &g, int precision, const mug
   }
 }
 
+// Launch groups (host only): the ultra-local loop rides in the first group; the displaced loops are sorted by
+// (length, direction) so that a group mixes directions.  What a group stages per eigenvector is the union of its loops'
+// shifted images of the tile: an x loop adds a few sites, a y loop a row or two, a z or t loop a whole copy of the tile.
+// Groups of one direction each (x:1..4 | y:1..4 | z:1..4 | t:1..4, the round-1 order) move the same total but leave the
+// z and t groups with 5x the tile per stage - bound by the L2 -> shared-memory path instead of the FP64 pipe - while
+// mixed groups all sit near 3.5x.  MUGIQ_B200_GROUP_BY_DIR=1 restores the per-direction order (for measurements).
+static int plan_make_groups(LoopPlan &pl) {
+  const int maxl = fused_max_loops_per_group(pl.g, pl.precision);
+  if (maxl < 0 || (maxl < 1 && pl.comps.size() > 1))
+    return set_error(MUGIQ_B200_EINVAL, "loop plan: lattice %dx%dx%dx%d does not fit the fused kernel's tile", pl.g.L[0],
+                     pl.g.L[1], pl.g.L[2], pl.g.L[3]);
+  std::vector<LoopPlan::Comp> order(pl.comps.begin(), pl.comps.end());
+  const bool by_dir = env_flag("MUGIQ_B200_GROUP_BY_DIR");
+  std::stable_sort(order.begin() + 1, order.end(), [by_dir](const LoopPlan::Comp &a, const LoopPlan::Comp &b) {
+    if (by_dir) {
+      if (a.dir != b.dir) return a.dir < b.dir;
+      if (a.sign != b.sign) return a.sign > b.sign;
+      return a.len < b.len;
+    }
+    if (a.len != b.len) return a.len < b.len;
+    if (a.dir != b.dir) return a.dir < b.dir;
+    return a.sign > b.sign;
+  });
+  pl.groups.clear();
+  const size_t per_loop = (size_t)16 * pl.g.volume;
+  size_t i = 1;  // order[0] is the ultra-local loop
+  do {
+    FusedGroup grp;
+    grp.nloops = maxl > 0 ? (int)std::min<size_t>(maxl, order.size() - i) : 0;
+    for (int j = 0; j < grp.nloops; j++) {
+      const LoopPlan::Comp &c = order[i + j];
+      grp.loop[j].W = c.W;
+      grp.loop[j].out_off = (long long)(per_loop * c.iL);
+      grp.loop[j].dir = c.dir;
+      grp.loop[j].sign = c.sign == MUGIQ_B200_SIGN_PLUS ? +1 : -1;
+      grp.loop[j].len = c.len;
+      grp.loop[j].pad_ = 0;
+    }
+    pl.groups.push_back(grp);
+    i += grp.nloops;
+  } while (i < order.size());
+  return MUGIQ_B200_OK;
+}
+
 // Builds the Wilson lines into pl.wbuf and the launch groups.
 static int plan_build(LoopPlan &pl, const void *gauge_d, cudaStream_t stream) {
   const size_t lfb = pl.link_field_bytes();
@@ -167,37 +211,7 @@ static int plan_build(LoopPlan &pl, const void *gauge_d, cudaStream_t stream) {
     else
       c.W = pl.wptr(find_w(pl, c.dir, MUGIQ_B200_SIGN_MINUS, c.len)->index);
   }
-  // launch groups: ultra-local first, then loops sorted by (direction, length) so that loops sharing shifted
-  // rows land in the same group
-  const int maxl = fused_max_loops_per_group(pl.g, pl.precision);
-  if (maxl < 0 || (maxl < 1 && pl.comps.size() > 1))
-    return set_error(MUGIQ_B200_EINVAL, "loop plan: lattice %dx%dx%dx%d does not fit the fused kernel's tile", pl.g.L[0],
-                     pl.g.L[1], pl.g.L[2], pl.g.L[3]);
-  std::vector<LoopPlan::Comp> order(pl.comps.begin(), pl.comps.end());
-  std::stable_sort(order.begin() + 1, order.end(), [](const LoopPlan::Comp &a, const LoopPlan::Comp &b) {
-    if (a.dir != b.dir) return a.dir < b.dir;
-    if (a.sign != b.sign) return a.sign > b.sign;
-    return a.len < b.len;
-  });
-  pl.groups.clear();
-  const size_t per_loop = (size_t)16 * pl.g.volume;
-  size_t i = 1;  // order[0] is the ultra-local loop
-  do {
-    FusedGroup grp;
-    grp.nloops = maxl > 0 ? (int)std::min<size_t>(maxl, order.size() - i) : 0;
-    for (int j = 0; j < grp.nloops; j++) {
-      const LoopPlan::Comp &c = order[i + j];
-      grp.loop[j].W = c.W;
-      grp.loop[j].out_off = (long long)(per_loop * c.iL);
-      grp.loop[j].dir = c.dir;
-      grp.loop[j].sign = c.sign == MUGIQ_B200_SIGN_PLUS ? +1 : -1;
-      grp.loop[j].len = c.len;
-      grp.loop[j].pad_ = 0;
-    }
-    pl.groups.push_back(grp);
-    i += grp.nloops;
-  } while (i < order.size());
-  return MUGIQ_B200_OK;
+  return plan_make_groups(pl);
 }
 
 static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
@@ -289,6 +303,7 @@ int mugiq_b200_loop_plan_create(mugiq_b200_loop_plan_t **plan, const void *gauge
   int rc = check_geom(geom, who);
   if (rc) return rc;
   if ((rc = check_entries(entries, nentries, who))) return rc;
+  if (nentries > 0 && (rc = check_geom_even(geom, who))) return rc;
   if (nentries > 0 && !gauge_d) return set_error(MUGIQ_B200_EINVAL, "%s: gauge_d is NULL", who);
   mugiq_b200_loop_plan_s *p = new mugiq_b200_loop_plan_s;
   plan_layout(p->pl, make_geom(geom->L), geom->precision, entries, nentries, true);
@@ -309,6 +324,24 @@ int mugiq_b200_loop_plan_create(mugiq_b200_loop_plan_t **plan, const void *gauge
   }
   *plan = p;
   return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int nentries, const mugiq_b200_geom_t *geom, int t_begin,
+                                  int t_end, int group, long long out[8]) {
+  const char *who = "mugiq_b200_fused_tiling_check";
+  int rc = check_geom(geom, who);
+  if (rc) return rc;
+  if ((rc = check_entries(entries, nentries, who))) return rc;
+  if (nentries > 0 && (rc = check_geom_even(geom, who))) return rc;
+  if (!out) return set_error(MUGIQ_B200_EINVAL, "%s: out is NULL", who);
+  LoopPlan pl;
+  plan_layout(pl, make_geom(geom->L), geom->precision, entries, nentries, true);
+  if ((rc = plan_make_groups(pl))) return rc;
+  if (group < 0) return (int)pl.groups.size();
+  if (group >= (int)pl.groups.size()) return set_error(MUGIQ_B200_EINVAL, "%s: the plan has %zu groups", who, pl.groups.size());
+  if (t_end < 0) t_end = geom->L[3];
+  if (t_begin < 0 || t_begin >= t_end || t_end > geom->L[3]) return set_error(MUGIQ_B200_EINVAL, "%s: bad time-slice range", who);
+  return fused_tiling_check(pl.groups[group], pl.g, pl.precision, t_begin, t_end, out);
 }
 
 int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan) {

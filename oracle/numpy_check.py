@@ -110,3 +110,26 @@ def momentum_projection(dataPos, mom, ftsign, L):
             for G in range(16):
                 out[im, (15 - G) + 16 * iL] = (-1 if G in minus else 1) * proj[G + 16 * iL]
     return out
+
+
+def momentum_projection_mm(dataPos, mom, ftsign, L, loops=None):
+    """Same result as momentum_projection for the loop slots `loops` (default: all), organised as one matrix product per
+    time-slice so that the BASELINE-sized buffers (24^3x48: 33 loops, 33 momenta) take seconds, not minutes:
+    out[im, G' + 16*k, t] for the k-th selected loop."""
+    nLoop = dataPos.shape[0]
+    loops = list(range(nLoop)) if loops is None else list(loops)
+    minus = {3, 6, 9, 11, 12, 14}
+    Lx, Ly, Lz, Lt = L
+    z, y, x = np.meshgrid(np.arange(Lz), np.arange(Ly), np.arange(Lx), indexing="ij")
+    ph = np.stack([np.exp(ftsign * 2j * np.pi * (p[0] * x / Lx + p[1] * y / Ly + p[2] * z / Lz)).ravel() for p in mom])  # [Nmom, V3]
+    order = lex_coords(L)  # eo index -> lexicographic index
+    inv = np.empty_like(order)
+    inv[order] = np.arange(order.size)  # lexicographic index -> eo index
+    inv = inv.reshape(Lt, Lx * Ly * Lz)
+    out = np.zeros((len(mom), 16 * len(loops), Lt), dtype=complex)
+    sign = np.array([-1.0 if G in minus else 1.0 for G in range(16)])
+    for k, iL in enumerate(loops):
+        for t in range(Lt):
+            proj = ph @ dataPos[iL][:, inv[t]].T  # [Nmom, 16]
+            out[:, 16 * k + 15 - np.arange(16), t] = proj * sign[None, :]
+    return out

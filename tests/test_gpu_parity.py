@@ -90,7 +90,7 @@ def test_displace_batch_tiles(ops, oracle, L, prec):
 
 
 @pytest.mark.parametrize("L", [(10, 6, 4, 4), (12, 5, 3, 4), (20, 7, 2, 2), (36, 3, 2, 2), (64, 2, 2, 2), (128, 2, 1, 2), (4, 16, 2, 2),
-                               (6, 9, 2, 2), (2, 3, 5, 2)])
+                               (6, 9, 2, 2), (2, 3, 5, 2), (20, 14, 2, 2), (36, 6, 2, 2), (2, 6, 10, 2), (128, 2, 2, 2)])
 def test_stage_kernels_tile_geometries(ops, oracle, L):
     """Tile selection of the bulk-TMA stage kernels over awkward extents: odd and prime Ly (one row per tile, or the whole
     y range in one tile with the wrap inside it), half-rows longer than the tile target, Lx/2 = 1, 3, 5, 9, 32, 64."""
@@ -99,12 +99,16 @@ def test_stage_kernels_tile_geometries(ops, oracle, L):
     U = synth.random_gauge(L, seed=45)
     gd = ops.gauge_upload(U, L)
     vd = [dev(v[i]) for i in range(n)]
-    for d in range(4):
-        for s in (0, 1):
-            outs = [torch.full_like(vd[0], 7.0) for _ in range(n)]
-            ops.displace_batch(outs, vd, gd, d, s, L)
-            for i in range(n):
-                assert rel_err(host(outs[i]), oracle.displace(v[i], U, d, s, L)) < 1e-14, (d, s, i)
+    if all(x % 2 == 0 for x in L):
+        for d in range(4):
+            for s in (0, 1):
+                outs = [torch.full_like(vd[0], 7.0) for _ in range(n)]
+                ops.displace_batch(outs, vd, gd, d, s, L)
+                for i in range(n):
+                    assert rel_err(host(outs[i]), oracle.displace(v[i], U, d, s, L)) < 1e-14, (d, s, i)
+    else:  # odd Ly / Lz / Lt: layout-only kernels below; displacements are rejected (QUDA needs even extents)
+        with pytest.raises(_lib.MugiqB200Error, match="must be even for displacements"):
+            ops.displace_batch([torch.empty_like(vd[0])], vd[:1], gd, 1, 1, L)
     V4 = v.shape[1]
     ref = np.zeros((16, V4), dtype=np.complex128)
     sig = [0.4, 0.5, 0.6]
@@ -227,7 +231,7 @@ def test_loop_accumulate_matches_oracle(ops, oracle, L, name):
     assert rel_err(host(out2), ref) < TOL_F64
 
 
-LOOP_LATTICES = [(16, 4, 4, 4), (12, 2, 4, 2), (6, 4, 2, 4), (24, 2, 2, 2), (4, 4, 4, 8), (8, 2, 2, 3)]
+LOOP_LATTICES = [(16, 4, 4, 4), (12, 2, 4, 2), (6, 4, 2, 4), (24, 2, 2, 2), (4, 4, 4, 8), (8, 2, 2, 6), (6, 6, 6, 2), (48, 2, 2, 2)]
 
 
 @pytest.mark.parametrize("L", LOOP_LATTICES)

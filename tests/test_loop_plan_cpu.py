@@ -61,12 +61,63 @@ def test_repeated_entries_are_copies_and_ultralocal_only_is_one_group():
     assert plan_info((8, 8, 8, 8), [], gauge=None) == {"nloop": 1, "computed": 1, "derived": 0, "groups": 1, "wilson_bytes": 0}
 
 
-def test_group_size_follows_the_lattice_row_length():
-    # Lx = 48: a tile row pair fills the 8 warps with fewer loops per group than Lx = 16
+def test_group_size_does_not_depend_on_the_row_length():
+    # a CTA works on a run of 32 consecutive checkerboard sites whatever Lx is: four loops per group everywhere
     wide = plan_info((48, 4, 4, 4), [(d, 1, 1, 1) for d in range(4)])
     narrow = plan_info((16, 4, 4, 4), [(d, 1, 1, 1) for d in range(4)])
-    assert narrow["groups"] == 1 and wide["groups"] >= narrow["groups"]
+    assert narrow["groups"] == 1 and wide["groups"] == 1
     assert wide["computed"] == narrow["computed"] == 5
+
+
+def tiling(L, entries, t_begin=0, t_end=-1, precision=8):
+    """mugiq_b200_fused_tiling_check for every launch group: [{run, units, nstages, stage_bytes, max_copies, mean_sites,
+    misses, bad_maps}]."""
+    lib = _lib.load()
+    g = _lib.make_geom(L, precision)
+    out = (C.c_longlong * 8)()
+    ngroups = lib.mugiq_b200_fused_tiling_check(_lib.entry_array(entries), len(entries), C.byref(g), t_begin, t_end, -1, out)
+    assert ngroups >= 1, lib.mugiq_b200_last_error()
+    res = []
+    for gi in range(ngroups):
+        assert lib.mugiq_b200_fused_tiling_check(_lib.entry_array(entries), len(entries), C.byref(g), t_begin, t_end, gi,
+                                                 out) == 0, lib.mugiq_b200_last_error()
+        res.append(dict(zip(("run", "units", "nstages", "stage_bytes", "max_copies", "mean_sites", "misses", "bad_maps"), out)))
+    return res
+
+
+UP_TO_4 = [(d, s, 1, 4) for d in range(4) for s in (1, 0)]
+
+
+@pytest.mark.parametrize("L,entries,t_range", [
+    ((4, 4, 4, 8), ONEHOP8 + [(2, 1, 2, 3)], (0, -1)),     # BASELINE configs[0] (+ the smoke test's longer hops)
+    ((16, 16, 16, 32), ONEHOP8, (0, -1)),                  # configs[1]
+    ((24, 24, 24, 48), UP_TO_4, (0, -1)),                  # configs[2]: Lx/2 = 12, runs of 2 2/3 rows
+    ((32, 32, 32, 64), [], (0, -1)),                       # configs[3]
+    ((48, 48, 48, 16), ONEHOP8, (2, 14)),                  # configs[4]: extended time slab, interior only
+    ((6, 6, 6, 6), UP_TO_4, (0, -1)),                      # Lx/2 = 3, volumeCB not a multiple of 32
+    ((2, 4, 6, 4), UP_TO_4, (1, 3)),                       # one site per half-row
+    ((12, 2, 2, 2), [(0, 1, 1, 7), (0, 0, 2, 9)], (0, -1)),  # x hops longer than the row
+])
+def test_every_thread_finds_its_sites_in_the_stage(L, entries, t_range):
+    """Host replay of what thread 0 of every CTA builds (the merged intervals of a stage) and of what every thread looks
+    up in it (own site, neighbour of every loop of the group): nothing may be missing, the maps must be sorted, disjoint,
+    16-byte granular and fit the sized ring."""
+    for prec in (8, 4):
+        for t in tiling(L, entries, *t_range, precision=prec):
+            assert t["misses"] == 0 and t["bad_maps"] == 0, t
+            assert t["run"] == 16 * t["units"] and t["nstages"] >= 2 and t["max_copies"] <= 64, t
+
+
+def test_runs_fill_every_lane_on_the_baseline_lattices():
+    """Groups of 4 loops: 32 sites per parity and CTA = 8 full warps, also where Lx/2 is 12 or 24 (whole-row tiles left
+    8 of 32 lanes idle there); what a stage holds stays near 3.5x the run for mixed-direction groups."""
+    for L, entries in [((16, 16, 16, 32), ONEHOP8), ((24, 24, 24, 48), UP_TO_4), ((48, 48, 48, 16), ONEHOP8)]:
+        for t in tiling(L, entries):
+            assert t["run"] == 32 and t["units"] == 2 and t["nstages"] >= 4, t
+            assert t["mean_sites"] <= 2 * 32 * 4.2, t
+    ul = tiling((32, 32, 32, 64), [])
+    assert ul == [dict(run=128, units=8, nstages=4, stage_bytes=128 * 2 * 192, max_copies=2, mean_sites=256, misses=0,
+                       bad_maps=0)]
 
 
 @pytest.mark.parametrize("entries,msg", [([(4, 1, 1, 1)], "direction"), ([(0, 2, 1, 1)], "sign"), ([(0, 1, 3, 1)], "start")])
