@@ -232,12 +232,7 @@ class Loop_Mugiq:
                     b1 = min(es.nEv, b0 + self.evec_batch)
                     # resident eigenvectors: the argument tables of a batch are built once and reused while the batch
                     # still consists of the same device buffers
-                    key = (b0, b1, es.eVecs[b0].data_ptr(), es.eVecs[b1 - 1].data_ptr())
-                    prep = self._prepared.get((b0, b1))
-                    if prep is None or prep[0] != key:
-                        prep = (key, plan.prepare(es.eVecs[b0:b1], es.eVals_sigma[b0:b1]))
-                        self._prepared[(b0, b1)] = prep
-                    plan.accumulate(self.dataPos_d, prep[1], accumulate=b0 > 0)
+                    plan.accumulate(self.dataPos_d, self._prepared_batch(plan, b0, b1, es.eVecs[b0:b1]), accumulate=b0 > 0)
             else:
                 self._accumulate_from_host(plan)
             # slots derived after the eigenvector sum (minus-direction partners, repeated entries); linear, so
@@ -259,6 +254,18 @@ class Loop_Mugiq:
             if p.doMomProj:
                 self.performMomentumProjection()
         return self
+
+    def _prepared_batch(self, plan, b0, b1, vecs):
+        """Argument tables (pointer array, sigma array) of the resident batch [b0, b1): built once and reused while the
+        batch consists of the same device buffers AND the same sigma values - the key holds every pointer and every
+        sigma, so refilled buffers keep their table but a changed eVals_sigma or a swapped tensor rebuilds it (the
+        reference re-reads sigma on every call, lib/loop_mugiq.cpp:479)."""
+        key = (tuple(v.data_ptr() for v in vecs), tuple(float(x) for x in self.eigsolve.eVals_sigma[b0:b1]))
+        prep = self._prepared.get((b0, b1))
+        if prep is None or prep[0] != key:
+            prep = (key, plan.prepare(vecs, self.eigsolve.eVals_sigma[b0:b1]))
+            self._prepared[(b0, b1)] = prep
+        return prep[1]
 
     def _mark(self, name):
         """MUGIQ_B200_TSPLIT_TRACE=1: CUDA-event + host time stamps at the phase boundaries of a T-split step."""
@@ -302,12 +309,7 @@ class Loop_Mugiq:
             ext = ts.finish_extend(cur)
             self._mark(f"halo wait {i}")
             if ts.peer is not None:  # the slabs are extended in place: same device buffers every time
-                key = (b0, b1, ext[0].data_ptr(), ext[-1].data_ptr())
-                prep = self._prepared.get((b0, b1))
-                if prep is None or prep[0] != key:
-                    prep = (key, plan.prepare(list(ext), es.eVals_sigma[b0:b1]))
-                    self._prepared[(b0, b1)] = prep
-                plan.accumulate(self.dataPosExt_d, prep[1], accumulate=b0 > 0)
+                plan.accumulate(self.dataPosExt_d, self._prepared_batch(plan, b0, b1, list(ext)), accumulate=b0 > 0)
             else:
                 plan.accumulate(self.dataPosExt_d, list(ext), es.eVals_sigma[b0:b1], accumulate=b0 > 0)
             self._mark(f"kernels {i}")

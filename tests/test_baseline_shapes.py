@@ -158,3 +158,36 @@ def test_config5_time_slab_48x48x48(oracle, monkeypatch, symmetry):
         for iL in computed:
             assert rel_err_t(pos[iL][:, interior], rk[iL][:, interior]) < TOL_F64
     plan.close()
+
+
+def test_resident_batches_follow_changed_sigma_and_refilled_buffers(oracle):
+    """Loop_Mugiq keeps the argument tables of a device-resident batch between calls.  Running again after the caller
+    changed eVals_sigma, refilled the same device buffers with new eigenvectors, or swapped a tensor must give the new
+    result (the reference re-reads sigma and the fields on every call, lib/loop_mugiq.cpp:478-483)."""
+    from mugiq_b200.loop import Loop_Mugiq, Eigsolve
+    L, nEv = (8, 4, 4, 8), 6
+    ev = synth.random_evecs_np(L, 2 * nEv, seed=205)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=205)
+    prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)])
+    prm.set_displacements("+x:1;-t:1,2")
+    es = Eigsolve([torch.from_numpy(ev[n]).cuda() for n in range(nEv)], sig, L)
+    loop = Loop_Mugiq(prm, es, evec_batch=4, copy_pos_to_host=False)
+    entries = loop.cPrm.entries()
+    loop.computeCoarseLoop()
+    assert rel_err(loop.dataPos_d.cpu().numpy(), oracle.compute_loop(ev[:nEv], sig, U, entries, L)) < TOL_F64
+    # 1. new sigma values, same buffers
+    sig2 = sig * 3.0 + 0.5
+    es.eVals_sigma = [float(x) for x in sig2]
+    loop.computeCoarseLoop()
+    assert rel_err(loop.dataPos_d.cpu().numpy(), oracle.compute_loop(ev[:nEv], sig2, U, entries, L)) < TOL_F64
+    # 2. same buffers refilled with other eigenvectors
+    for n in range(nEv):
+        es.eVecs[n].copy_(torch.from_numpy(ev[nEv + n]))
+    loop.computeCoarseLoop()
+    assert rel_err(loop.dataPos_d.cpu().numpy(), oracle.compute_loop(ev[nEv:], sig2, U, entries, L)) < TOL_F64
+    # 3. an interior tensor of a batch replaced by another allocation
+    es.eVecs[2] = torch.from_numpy(ev[0]).cuda()
+    mixed = np.concatenate([ev[nEv:nEv + 2], ev[0:1], ev[nEv + 3:]])
+    loop.computeCoarseLoop()
+    assert rel_err(loop.dataPos_d.cpu().numpy(), oracle.compute_loop(mixed, sig2, U, entries, L)) < TOL_F64
