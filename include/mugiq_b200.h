@@ -195,6 +195,9 @@ int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan);
 int mugiq_b200_loop_plan_nloop(const mugiq_b200_loop_plan_t *plan);
 int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed, int *nderived, int *ngroups,
                               long long *wilson_bytes);
+/* The dataPos slots (iL) accumulate() writes - what a cross-rank sum has to cover; the others are filled by finalize().
+ * Writes at most max_slots of them, returns how many there are. */
+int mugiq_b200_loop_plan_computed_slots(const mugiq_b200_loop_plan_t *plan, int *slots, int max_slots);
 /* Lattice-T split (BASELINE config 5): a rank runs the plan on its time slab EXTENDED by halo slices.
  *   set_t_range : accumulate() computes dataPos only on the time-slices [t_begin, t_end) of the plan's lattice (the
  *                 rank's interior) and merely reads the others; finalize() still spans the whole lattice.
@@ -253,6 +256,39 @@ int mugiq_b200_phase_matrix_eo(void *phase_eo_d, const int *mom_h, int Nmom, int
 long long mugiq_b200_momproj_pos_workspace_bytes(const mugiq_b200_geom_t *geom, int nLoop, int Nmom);
 int mugiq_b200_momproj_pos(void *mom_d, const void *dataPos_d, const void *phase_eo_d, int nLoop, int Nmom,
                            const mugiq_b200_geom_t *geom, void *workspace_d, void *stream);
+
+/* ---- eigenvector shards: the cross-GPU sum of the loop buffer --------------------------------------------------- */
+/* One process per GPU; every rank runs the loop plan on its shard of the eigenvectors (the gauge field is replicated),
+ * then the loop buffer is summed over the ranks with NCCL over NVLink / NVSwitch.  Replaces the reference's D2H copy +
+ * MPI_Reduce over COMM_SPACE + MPI_Gather over COMM_TIME + MPI_Bcast on host buffers (lib/loop_mugiq.cpp:386-424) and
+ * the MPI_Comm_split pair of Loop_Mugiq::setupComms (:62-88).  NCCL is bound at run time (the process's own
+ * libnccl.so.2); the caller moves the 128-byte id from rank 0 to the other ranks by whatever transport it has (the
+ * Python front end: its process group; the C++ front end: a file).
+ *   comm_unique_id : rank 0 makes the id (ncclGetUniqueId)
+ *   comm_create    : collective over all `size` ranks, on the calling thread's current CUDA device
+ *   allreduce      : in-place sum of `count` REAL numbers of the given precision, asynchronous on `stream`
+ *   allgather      : every rank contributes `bytes` bytes, rank-major result (the COMM_TIME gather of a lattice-T split)
+ *   allreduce_pos  : in-place sum of the time-slices [t_begin, t_end) (t_end < 0: all) of the loop slots slots_h[0..nslots)
+ *                    of a position-space buffer - the "per-time-slice loop buffer" - as one grouped NCCL launch
+ *   loop_plan_accumulate_allreduce : mugiq_b200_loop_plan_accumulate for the LAST (or only) eigenvector batch of a
+ *                    sharded run, fused with the sum of every slot the plan computes: the lattice is processed in
+ *                    `nchunks` time-slice chunks, and the all-reduce of chunk k runs on a high-priority side stream
+ *                    while the kernels of chunk k+1 compute (only the last chunk's sum is exposed).  On return,
+ *                    work enqueued on `stream` sees the summed buffer; call loop_plan_finalize afterwards (the derived
+ *                    slots are linear in the computed ones, so they need no sum of their own). */
+#define MUGIQ_B200_COMM_ID_BYTES 128
+typedef struct mugiq_b200_comm_s mugiq_b200_comm_t;
+int mugiq_b200_comm_unique_id(void *id128);
+int mugiq_b200_comm_create(mugiq_b200_comm_t **comm, const void *id128, int rank, int size);
+int mugiq_b200_comm_destroy(mugiq_b200_comm_t *comm);
+int mugiq_b200_comm_info(const mugiq_b200_comm_t *comm, int *rank, int *size, int *nccl_version);
+int mugiq_b200_allreduce(void *buf_d, long long count, int precision, mugiq_b200_comm_t *comm, void *stream);
+int mugiq_b200_allgather(void *recv_d, const void *send_d, long long bytes, mugiq_b200_comm_t *comm, void *stream);
+int mugiq_b200_allreduce_pos(void *dataPos_d, const int *slots_h, int nslots, int t_begin, int t_end,
+                             const mugiq_b200_geom_t *geom, mugiq_b200_comm_t *comm, void *stream);
+int mugiq_b200_loop_plan_accumulate_allreduce(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, const void *const *evec_d,
+                                              const double *sigma_h, int nvec, int accumulate, mugiq_b200_comm_t *comm,
+                                              int nchunks, void *stream);
 
 /* ---- lattice-T split: halo slices over NVLink peer memory ------------------------------------------------------ */
 /* Replaces, for a partitioned t direction, ColorSpinorField::exchangeGhost (lib/contract_wrappers.cu:166-174: one

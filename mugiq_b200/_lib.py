@@ -14,6 +14,7 @@ ORDER_SITE, ORDER_FLOAT2, ORDER_FLOAT4 = 0, 2, 4
 DIR_X, DIR_Y, DIR_Z, DIR_T = 0, 1, 2, 3
 SIGN_MINUS, SIGN_PLUS = 0, 1
 MAX_ENTRIES = 64
+COMM_ID_BYTES = 128
 
 
 class Geom(C.Structure):
@@ -66,6 +67,15 @@ SYMBOLS = {
     "mugiq_b200_peer_free": (_i, [_vp]),
     "mugiq_b200_halo_push_t": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "mugiq_b200_fused_tiling_check": (_i, [_pe, _i, _pg, _i, _i, _i, C.POINTER(_ll)]),
+    "mugiq_b200_loop_plan_computed_slots": (_i, [_vp, _pi, _i]),
+    "mugiq_b200_comm_unique_id": (_i, [_vp]),
+    "mugiq_b200_comm_create": (_i, [C.POINTER(_vp), _vp, _i, _i]),
+    "mugiq_b200_comm_destroy": (_i, [_vp]),
+    "mugiq_b200_comm_info": (_i, [_vp, _pi, _pi, _pi]),
+    "mugiq_b200_allreduce": (_i, [_vp, _ll, _i, _vp, _vp]),
+    "mugiq_b200_allgather": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "mugiq_b200_allreduce_pos": (_i, [_vp, _pi, _i, _i, _i, _pg, _vp, _vp]),
+    "mugiq_b200_loop_plan_accumulate_allreduce": (_i, [_vp, _vp, _pvp, _pd, _i, _i, _vp, _i, _vp]),
     "mugiq_b200_loop_plan_set_t_range": (_i, [_vp, _i, _i]),
     "mugiq_b200_loop_plan_t_halo": (_i, [_vp, _pi, _pi, _pi]),
     "mugiq_b200_loop_plan_accumulate": (_i, [_vp, _vp, _pvp, _pd, _i, _i, _vp]),

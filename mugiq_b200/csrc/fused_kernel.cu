@@ -76,22 +76,21 @@ __host__ __device__ inline int wrap(int a, int n) {
   return a < 0 ? a + n : a;
 }
 
-// insert [lo, hi) of parity par into the sorted list of disjoint intervals, merging what overlaps or adjoins
-__host__ __device__ inline void iv_insert(StageMap &m, int par, int lo, int hi) {
+// insert [lo, hi) into the sorted list of disjoint intervals m.lo/m.hi[0..m.n), merging what overlaps or adjoins
+__host__ __device__ inline void iv_insert(StageMap &m, int lo, int hi) {
   if (lo >= hi) return;
   int i = 0;
-  while (i < m.n && (m.par[i] < par || (m.par[i] == par && m.hi[i] < lo))) i++;
-  if (i < m.n && m.par[i] == par && m.lo[i] <= hi) {  // touches interval i: grow it, swallow the followers it reaches
+  while (i < m.n && m.hi[i] < lo) i++;
+  if (i < m.n && m.lo[i] <= hi) {  // touches interval i: grow it, swallow the followers it reaches
     if (lo < m.lo[i]) m.lo[i] = lo;
     if (hi > m.hi[i]) m.hi[i] = hi;
     int k = i + 1;
-    while (k < m.n && m.par[k] == par && m.lo[k] <= m.hi[i]) {
+    while (k < m.n && m.lo[k] <= m.hi[i]) {
       if (m.hi[k] > m.hi[i]) m.hi[i] = m.hi[k];
       k++;
     }
     if (k > i + 1) {
       for (int d = i + 1, s = k; s < m.n; d++, s++) {
-        m.par[d] = m.par[s];
         m.lo[d] = m.lo[s];
         m.hi[d] = m.hi[s];
       }
@@ -99,16 +98,14 @@ __host__ __device__ inline void iv_insert(StageMap &m, int par, int lo, int hi) 
     }
     return;
   }
-  if (m.n == kMaxIv) {
+  if (2 * (m.n + 1) > kMaxIv) {  // the list is replicated for the second parity at the end
     m.overflow = 1;
     return;
   }
   for (int d = m.n; d > i; d--) {
-    m.par[d] = m.par[d - 1];
     m.lo[d] = m.lo[d - 1];
     m.hi[d] = m.hi[d - 1];
   }
-  m.par[i] = par;
   m.lo[i] = lo;
   m.hi[i] = hi;
   m.n++;
@@ -117,59 +114,88 @@ __host__ __device__ inline void iv_insert(StageMap &m, int par, int lo, int hi) 
 // Stage of the run [c0, c1) (both parities) for the loops of grp: the run itself plus, per loop, the image of every row
 // piece of the run.  A y/z/t shift maps the piece [a, b) of row r to the same positions of the shifted row; an x shift
 // of length k keeps the row and moves the half-row index by at most ceil(k/2) (periodic inside the row).  Both
-// parities are staged for every image: a site's neighbour has parity p ^ (k & 1) and both own parities are in the tile.
+// parities are staged for every image (a site's neighbour has parity p ^ (k & 1) and both own parities are in the tile),
+// so the interval list is built once and replicated.  Images of consecutive row pieces usually adjoin: they are joined
+// before they are inserted.
 __host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &grp, const LatGeom &g, int site_bytes, int c0,
                                                 int c1) {
   m.n = 0;
   m.overflow = 0;
   const int Lh = g.Lh;
-  for (int p = 0; p < 2; p++) iv_insert(m, p, c0, c1);
+  iv_insert(m, c0, c1);
   for (int j = 0; j < grp.nloops; j++) {
     const FusedLoop &lp = grp.loop[j];
     const int sh = lp.sign * lp.len;
+    int plo = 0, phi = 0;  // pending image interval
     for (int c = c0; c < c1;) {
       const int row = c / Lh, a = c - row * Lh;
       int b = a + (c1 - c);
       if (b > Lh) b = Lh;
       const int base = row * Lh;
+      int lo, hi;
       if (lp.dir == 0) {
         const int h = (lp.len + 1) >> 1;
-        int lo = a - h, hi = b + h;
+        lo = a - h;
+        hi = b + h;
         if (hi - lo >= Lh) {
           lo = 0;
           hi = Lh;
         }
-        for (int p = 0; p < 2; p++) {
-          if (lo < 0) iv_insert(m, p, base + lo + Lh, base + Lh);
-          if (hi > Lh) iv_insert(m, p, base, base + hi - Lh);
-          iv_insert(m, p, base + (lo < 0 ? 0 : lo), base + (hi > Lh ? Lh : hi));
+        if (lo < 0) {
+          iv_insert(m, base + lo + Lh, base + Lh);
+          lo = 0;
         }
+        if (hi > Lh) {
+          iv_insert(m, base, base + hi - Lh);
+          hi = Lh;
+        }
+        lo += base;
+        hi += base;
       } else {
         int y = row % g.L[1], z = (row / g.L[1]) % g.L[2], t = row / (g.L[1] * g.L[2]);
         if (lp.dir == 1) y = wrap(y + sh, g.L[1]);
         if (lp.dir == 2) z = wrap(z + sh, g.L[2]);
         if (lp.dir == 3) t = wrap(t + sh, g.L[3]);
         const int nb = (y + g.L[1] * (z + g.L[2] * t)) * Lh;
-        for (int p = 0; p < 2; p++) iv_insert(m, p, nb + a, nb + b);
+        lo = nb + a;
+        hi = nb + b;
+      }
+      if (lo <= phi && plo <= hi && phi > plo) {  // adjoins or overlaps the pending image: join
+        if (lo < plo) plo = lo;
+        if (hi > phi) phi = hi;
+      } else {
+        iv_insert(m, plo, phi);
+        plo = lo;
+        phi = hi;
       }
       c += b - a;
     }
+    iv_insert(m, plo, phi);
   }
+  // parity 0 block, then the same intervals for parity 1
+  const int n = m.n;
   int off = 0;
-  for (int i = 0; i < m.n; i++) {
-    m.soff[i] = off;
-    m.cp_soff[i] = off * site_bytes;
-    m.cp_goff16[i] = (int)((((long long)m.par[i] * g.volumeCB + m.lo[i]) * site_bytes) >> 4);
-    m.cp_bytes[i] = (m.hi[i] - m.lo[i]) * site_bytes;
-    off += m.hi[i] - m.lo[i];
-  }
+  for (int p = 0; p < 2; p++)
+    for (int i = 0; i < n; i++) {
+      const int k = p * n + i;
+      m.par[k] = p;
+      m.lo[k] = m.lo[i];
+      m.hi[k] = m.hi[i];
+      m.soff[k] = off;
+      m.cp_soff[k] = off * site_bytes;
+      m.cp_goff16[k] = (int)((((long long)p * g.volumeCB + m.lo[i]) * site_bytes) >> 4);
+      m.cp_bytes[k] = (m.hi[i] - m.lo[i]) * site_bytes;
+      off += m.hi[i] - m.lo[i];
+    }
+  m.n = 2 * n;
   m.sites = off;
 }
 
 // position (in sites) of checkerboard site cb of parity par inside the stage; -1 if the stage does not hold it
 __host__ __device__ inline int stage_site(const StageMap &m, int par, int cb) {
-  for (int i = 0; i < m.n; i++)
-    if (m.par[i] == par && m.lo[i] <= cb && cb < m.hi[i]) return m.soff[i] + cb - m.lo[i];
+  const int n = m.n >> 1;
+  for (int i = par * n; i < (par + 1) * n; i++)
+    if (m.lo[i] <= cb && cb < m.hi[i]) return m.soff[i] + cb - m.lo[i];
   return -1;
 }
 

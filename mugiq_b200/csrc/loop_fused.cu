@@ -18,42 +18,9 @@
 #include <vector>
 
 #include "fused.cuh"
+#include "plan.cuh"
 
 namespace mugiq_b200 {
-
-struct LoopPlan {
-  struct Comp {  // a loop computed by the fused kernel
-    int dir, sign, len;
-    int iL;         // slot of dataPos it is written to
-    const void *W;  // Wilson line (device), nullptr for the ultra-local loop
-  };
-  struct Derive {  // a slot filled after the eigenvector sum
-    int kind;      // 0 = copy of slot src, 1 = minus from plus
-    int dst, src, dir, len;
-  };
-  LatGeom g;
-  int precision;
-  int nLoop;
-  bool symmetric;
-  int t_begin = 0, t_end = -1;  // time-slices the fused kernels compute (-1: all): interior of a lattice-T split slab
-  std::vector<Comp> comps;
-  std::vector<Derive> derives;
-  std::vector<int> zero_slots;  // slots no hop reaches (start < 1): stay zero, as in the reference
-  std::vector<FusedGroup> groups;  // displaced loops; the ultra-local loop rides in groups[0]
-  // Wilson-line storage
-  struct WField {
-    int dir, sign, len;
-    size_t index;  // field index inside wbuf
-  };
-  std::vector<WField> wfields;
-  size_t nW = 0;
-  void *wbuf = nullptr;
-  bool own_wbuf = false;
-
-  size_t link_field_bytes() const { return (size_t)g.volume * kLinkLen * 2 * prec_bytes(precision); }
-  size_t loop_bytes() const { return (size_t)16 * g.volume * 2 * prec_bytes(precision); }
-  const void *wptr(size_t index) const { return static_cast<const char *>(wbuf) + index * link_field_bytes(); }
-};
 
 static bool env_flag(const char *name) {
   const char *e = getenv(name);
@@ -214,10 +181,11 @@ static int plan_build(LoopPlan &pl, const void *gauge_d, cudaStream_t stream) {
   return plan_make_groups(pl);
 }
 
-static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
-                           int accumulate, cudaStream_t stream) {
+// Contribution of the given eigenvectors to every loop the plan computes, on the time-slices [t0, t1) only.
+int plan_accumulate_range(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
+                          int accumulate, int t0, int t1, bool zero_unreached, cudaStream_t stream) {
   char *pos = static_cast<char *>(dataPos_d);
-  if (!accumulate)
+  if (!accumulate && zero_unreached)
     for (int z : pl.zero_slots) MUGIQ_CUDA_CHECK(cudaMemsetAsync(pos + (size_t)z * pl.loop_bytes(), 0, pl.loop_bytes(), stream));
   for (int done = 0; done < nvec; done += kFusedMaxVec) {
     FusedVecTable vt;
@@ -229,11 +197,16 @@ static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *cons
     for (size_t gi = 0; gi < pl.groups.size(); gi++) {
       // slot 0 (ultra-local) is accumulated by the first group
       int rc = fused_group_launch(dataPos_d, pl.groups[gi], gi == 0 ? 0 : -1, vt, accumulate || done > 0, pl.g,
-                                  pl.precision, stream, pl.t_begin, pl.t_end);
+                                  pl.precision, stream, t0, t1);
       if (rc) return rc;
     }
   }
   return MUGIQ_B200_OK;
+}
+
+static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
+                           int accumulate, cudaStream_t stream) {
+  return plan_accumulate_range(pl, dataPos_d, evec_d, sigma_h, nvec, accumulate, pl.t_begin, pl.t_end, true, stream);
 }
 
 static int plan_finalize(const LoopPlan &pl, void *dataPos_d, int accumulate, cudaStream_t stream) {
@@ -292,6 +265,10 @@ using namespace mugiq_b200;
 struct mugiq_b200_loop_plan_s {
   LoopPlan pl;
 };
+
+namespace mugiq_b200 {
+const LoopPlan &plan_of(const mugiq_b200_loop_plan_t *plan) { return plan->pl; }
+}  // namespace mugiq_b200
 
 extern "C" {
 
@@ -364,6 +341,13 @@ int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed
   if (ngroups) *ngroups = (int)plan->pl.groups.size();
   if (wilson_bytes) *wilson_bytes = (long long)(plan->pl.nW * plan->pl.link_field_bytes());
   return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_loop_plan_computed_slots(const mugiq_b200_loop_plan_t *plan, int *slots, int max_slots) {
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_loop_plan_computed_slots: plan is NULL");
+  const int n = (int)plan->pl.comps.size();
+  for (int i = 0; slots && i < n && i < max_slots; i++) slots[i] = plan->pl.comps[i].iL;
+  return n;
 }
 
 int mugiq_b200_loop_plan_set_t_range(mugiq_b200_loop_plan_t *plan, int t_begin, int t_end) {

@@ -30,7 +30,8 @@ ProfState &st() {
   return s;
 }
 const char *kNames[K_COUNT] = {"contract_batch", "displace",      "loop_fused", "wilson_line", "minus_from_plus",
-                               "reorder_mapgamma", "phase_matrix", "momproj",    "splitk_reduce", "convert_spinor", "halo_push"};
+                               "reorder_mapgamma", "phase_matrix", "momproj",    "splitk_reduce", "convert_spinor", "halo_push",
+                               "allreduce"};
 }  // namespace
 
 const char *kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kNames[id] : "?"; }

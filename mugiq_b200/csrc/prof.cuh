@@ -20,6 +20,7 @@ enum KernelId {
   K_SPLITK_REDUCE,    // splitk_reduce_kernel
   K_CONVERT,          // convert_spinor_kernel
   K_HALO_PUSH,        // halo_push_kernel / copy-engine 2-D copy into a time neighbour's slabs (peer.cu)
+  K_ALLREDUCE,        // NCCL all-reduce of (a time-slice range of) the loop buffer (comm.cu); NCCL's kernel, not ours
   K_COUNT
 };
 

@@ -247,6 +247,7 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   std::vector<const void *> ptr(batch), src(batch);
   std::vector<void *> stage(batch);
   std::vector<double> sigma(batch);
+  const bool sharded = getLoopComm() && mugiqCommSize(getLoopComm()) > 1;
   for (int n0 = 0; n0 < nEv; n0 += batch) {
     const int nb = std::min(batch, nEv - n0);
     for (int i = 0; i < nb; i++) {
@@ -259,17 +260,19 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
     }
     if (native)  // the whole batch in one launch
       MUGIQ_CHECK(mugiq_b200_ingest_spinor_batch(stage.data(), src.data(), nb, abi_order(fieldOrder), &geom, nullptr));
-    MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0, nullptr));
+    // eigenvector shards (one process per GPU): the last batch's kernels run chunk by chunk in t, each chunk's cross-rank
+    // sum over NVLink overlapping the next chunk's kernels (replaces the host-staged MPI collectives, lib/loop_mugiq.cpp:386-424)
+    if (sharded && n0 + nb >= nEv)
+      MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate_allreduce(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0,
+                                                            mugiqCommHandle(getLoopComm()), 8, nullptr));
+    else
+      MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0, nullptr));
     printfQuda("%s: Loop trace for eigenvectors %04d - %04d completed\n", __func__, n0, n0 + nb - 1);
   }
+  if (sharded) printfQuda("%s: Loop buffer summed over %d ranks\n", __func__, mugiqCommSize(getLoopComm()));
+  // slots derived from computed ones (minus-direction partners, repeated entries) are linear in them: filled after the sum
   MUGIQ_CHECK(mugiq_b200_loop_plan_finalize(plan, dataPos_d, 0, nullptr));
   if (!displace) mugiq_b200_loop_plan_destroy(plan);
-
-  // eigenvector shards (one process per GPU): sum the position-space buffer over the ranks on the device
-  if (getLoopComm() && mugiqCommSize(getLoopComm()) > 1) {
-    mugiqCommAllReduceSum(getLoopComm(), dataPos_d, (size_t)2 * nElemPosLoc, precision_of<Float>());
-    printfQuda("%s: Loop buffer summed over %d ranks\n", __func__, mugiqCommSize(getLoopComm()));
-  }
 
   // always copy the device position-space buffer to the host
   HOST_CUDA(cudaMemcpy(dataPos, dataPos_d, SizeCplxFloat * nElemPosLoc, cudaMemcpyDeviceToHost));

@@ -122,9 +122,18 @@ class Loop_Mugiq:
     """
 
     def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64,
-                 stream_batch=16, copy_pos_to_host=True, fused_momproj=True, tsplit=None):
+                 stream_batch=16, copy_pos_to_host=True, fused_momproj=True, tsplit=None, comm=None, reduce_pos=None,
+                 allreduce_chunks=8):
         self.eigsolve = eigsolve_
         self.group = group
+        # ops.Comm over the same ranks as `group`: the cross-rank sums then go through the library's own NCCL calls
+        # (mugiq_b200_allreduce*), the position-space one overlapped with the kernels chunk by chunk; without it they
+        # are torch.distributed all-reduces after the kernels
+        self.comm = comm
+        # eigenvector shards: sum the position-space buffer over the ranks (True), or only the projected one (False);
+        # None = the position-space buffer exactly when it is needed on every rank (host copy, or no projection)
+        self.reduce_pos = reduce_pos
+        self.allreduce_chunks = int(allreduce_chunks)
         self.evec_batch = int(evec_batch)      # eigenvectors per C-ABI call when they are device resident
         self.stream_batch = int(stream_batch)  # eigenvectors per H2D staging buffer when they live on the host
         # the reference always copies dataPos_d to the host (lib/loop_mugiq.cpp:512); a caller that only wants
@@ -227,24 +236,34 @@ class Loop_Mugiq:
             if self.tsplit is not None:
                 self._accumulate_tsplit(plan)
                 return self._finish_tsplit()
-            if es.eVecs[0].is_cuda:
-                for b0 in range(0, es.nEv, self.evec_batch):
-                    b1 = min(es.nEv, b0 + self.evec_batch)
-                    # resident eigenvectors: the argument tables of a batch are built once and reused while the batch
-                    # still consists of the same device buffers
-                    plan.accumulate(self.dataPos_d, self._prepared_batch(plan, b0, b1, es.eVecs[b0:b1]), accumulate=b0 > 0)
-            else:
-                self._accumulate_from_host(plan)
-            # slots derived after the eigenvector sum (minus-direction partners, repeated entries); linear, so
-            # it commutes with the cross-rank sum below
-            plan.finalize(self.dataPos_d)
             # eigenvector shards: the position-space buffer is summed over the group only when it is
             # needed on every rank (host copy requested or no momentum projection); otherwise the
             # projection, which is linear, runs on the partial sums and the small dataMom is reduced
-            self._reduce_mom = self.group is not None and p.doMomProj and not self.copy_pos_to_host
-            if self.group is not None and not self._reduce_mom:
+            sharded = self.group is not None or self.comm is not None
+            want_pos = self.reduce_pos if self.reduce_pos is not None else (self.copy_pos_to_host or not p.doMomProj)
+            self._reduce_mom = sharded and p.doMomProj and not want_pos
+            reduce_pos = sharded and not self._reduce_mom
+            fused_reduce = reduce_pos and self.comm is not None   # sum overlapped with the kernels of the last batch
+            if es.eVecs[0].is_cuda:
+                starts = list(range(0, es.nEv, self.evec_batch))
+                for b0 in starts:
+                    b1 = min(es.nEv, b0 + self.evec_batch)
+                    prep = self._prepared_batch(plan, b0, b1, es.eVecs[b0:b1])
+                    if fused_reduce and b0 == starts[-1]:
+                        plan.accumulate_allreduce(self.dataPos_d, prep, self.comm, accumulate=b0 > 0,
+                                                  nchunks=self.allreduce_chunks)
+                    else:
+                        plan.accumulate(self.dataPos_d, prep, accumulate=b0 > 0)
+            else:
+                self._accumulate_from_host(plan)
+                if fused_reduce:
+                    self.comm.allreduce_pos(self.dataPos_d, plan.computed_slots(), self.L)
+            if reduce_pos and not fused_reduce:
                 import torch.distributed as dist
                 dist.all_reduce(torch.view_as_real(self.dataPos_d), op=dist.ReduceOp.SUM, group=self.group)
+            # slots derived after the eigenvector sum (minus-direction partners, repeated entries): linear in the
+            # computed slots, so they are filled after the cross-rank sum and need none of their own
+            plan.finalize(self.dataPos_d)
             # "Always copy the device position-space buffer to the host" (lib/loop_mugiq.cpp:512)
             if self.copy_pos_to_host:
                 if self.dataPos is None:
@@ -418,8 +437,11 @@ class Loop_Mugiq:
             M, N, K = p.locT * p.nData, p.Nmom, p.locV3
             self.dataMom_d = ops.momproj(self.dataPosMP_d, self.phaseMatrix_d, M, N, K).reshape(p.Nmom, p.nData, p.locT)
         if getattr(self, "_reduce_mom", False):
-            import torch.distributed as dist
-            dist.all_reduce(torch.view_as_real(self.dataMom_d), op=dist.ReduceOp.SUM, group=self.group)
+            if self.comm is not None:
+                self.comm.allreduce(self.dataMom_d)
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(torch.view_as_real(self.dataMom_d), op=dist.ReduceOp.SUM, group=self.group)
         self.dataMom_h = self.dataMom_d.cpu()
         # single spatial block: MPI_Reduce over COMM_SPACE is the identity
         self.dataMom = self.dataMom_h

@@ -226,6 +226,13 @@ class LoopPlan:
         check(_lib.load().mugiq_b200_loop_plan_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(w)))
         return {"computed": a.value, "derived": b.value, "groups": c.value, "wilson_bytes": w.value}
 
+    def computed_slots(self):
+        """dataPos slots accumulate() writes (the others are derived by finalize())."""
+        n = check(_lib.load().mugiq_b200_loop_plan_computed_slots(self._h, None, 0))
+        arr = (C.c_int * n)()
+        check(_lib.load().mugiq_b200_loop_plan_computed_slots(self._h, arr, n))
+        return list(arr)
+
     def set_t_range(self, t_begin, t_end):
         """accumulate() computes only the time-slices [t_begin, t_end) (interior of a lattice-T split slab)."""
         check(_lib.load().mugiq_b200_loop_plan_set_t_range(self._h, int(t_begin), int(t_end)))
@@ -251,6 +258,16 @@ class LoopPlan:
         with torch.cuda.device(dataPos.device):
             check(_lib.load().mugiq_b200_loop_plan_accumulate(self._h, dataPos.data_ptr(), prep.ptrs, prep.sigma, prep.n,
                                                               int(bool(accumulate)), _stream()))
+        return dataPos
+
+    def accumulate_allreduce(self, dataPos, evecs, comm, sigma=None, accumulate=False, nchunks=8):
+        """accumulate() for the last (or only) batch of a rank's eigenvector shard, fused with the NCCL sum of every slot
+        the plan computes: time-slice chunk k is summed on the communicator's side stream while chunk k+1 computes."""
+        prep = evecs if isinstance(evecs, PreparedBatch) else self.prepare(evecs, sigma)
+        _dev(dataPos)
+        with torch.cuda.device(dataPos.device):
+            check(_lib.load().mugiq_b200_loop_plan_accumulate_allreduce(self._h, dataPos.data_ptr(), prep.ptrs, prep.sigma, prep.n,
+                                                                        int(bool(accumulate)), comm._h, int(nchunks), _stream()))
         return dataPos
 
     def finalize(self, dataPos, accumulate=False):
@@ -341,6 +358,65 @@ def momproj_pos(dataPos, phase_eo, nLoop, L, workspace=None):
         check(_lib.load().mugiq_b200_momproj_pos(out.data_ptr(), dataPos.data_ptr(), phase_eo.data_ptr(), int(nLoop), int(nmom),
                                                  C.byref(geom), workspace.data_ptr(), _stream()))
     return out
+
+
+# ---- eigenvector shards: NCCL communicator of the library (mugiq_b200_comm_*, mugiq_b200_allreduce*) ----------------
+class Comm:
+    """mugiq_b200_comm_t over the ranks of a torch.distributed process group: rank 0 makes the NCCL id, the group
+    carries its 128 bytes to the others, every rank joins on its current CUDA device.  The library binds the NCCL
+    already loaded in the process (torch's), so there is one NCCL per process."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        if self.rank == 0:
+            check(_lib.load().mugiq_b200_comm_unique_id(ident))
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.load().mugiq_b200_comm_create(C.byref(self._h), C.c_char_p(box[0]), self.rank, self.size))
+
+    def info(self):
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        check(_lib.load().mugiq_b200_comm_info(self._h, C.byref(r), C.byref(n), C.byref(v)))
+        return {"rank": r.value, "size": n.value, "nccl_version": v.value}
+
+    def allreduce(self, t):
+        """In-place sum of a real or complex tensor over the ranks, on the current stream."""
+        _dev(t)
+        count = t.numel() * (2 if t.is_complex() else 1)
+        with torch.cuda.device(t.device):
+            check(_lib.load().mugiq_b200_allreduce(t.data_ptr(), count, _prec(t), self._h, _stream()))
+        return t
+
+    def allreduce_pos(self, dataPos, slots, L, t_begin=0, t_end=-1):
+        """In-place sum of the time-slices [t_begin, t_end) of the loop slots `slots` of dataPos [nLoop, 16, V4]."""
+        _dev(dataPos)
+        geom = make_geom(L, _prec(dataPos))
+        arr = (C.c_int * len(slots))(*[int(x) for x in slots])
+        with torch.cuda.device(dataPos.device):
+            check(_lib.load().mugiq_b200_allreduce_pos(dataPos.data_ptr(), arr, len(slots), int(t_begin), int(t_end),
+                                                       C.byref(geom), self._h, _stream()))
+        return dataPos
+
+    def allgather(self, send):
+        _dev(send)
+        recv = torch.empty((self.size,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        with torch.cuda.device(send.device):
+            check(_lib.load().mugiq_b200_allgather(recv.data_ptr(), send.data_ptr(), send.numel() * send.element_size(), self._h,
+                                                   _stream()))
+        return recv
+
+    def close(self):
+        if self._h:
+            with torch.cuda.device(self.device):
+                _lib.load().mugiq_b200_comm_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 # ---- NVLink peer memory for the lattice-T split (mugiq_b200_peer_*, mugiq_b200_halo_push_t) -------------------------
