@@ -222,6 +222,34 @@ int mugiq_b200_loop_plan_finalize(const mugiq_b200_loop_plan_t *plan, void *data
 int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int nentries, const mugiq_b200_geom_t *geom,
                                   int t_begin, int t_end, int group, long long out[8]);
 
+/* ---- streamed eigenvector feed of a loop plan --------------------------------------------------------------------- */
+/* The producer/consumer form of the eigenvector loop: the reference makes the fine eigenvector right before it is used,
+ * `prolongateEvec(fineEvecL, eVecs[n])` through the multigrid transfer operators or a field copy (lib/loop_mugiq.cpp:276-319,
+ * 478-483).  1000-2000 fine eigenvectors of the BASELINE lattices do not fit a GPU, so the fused path takes them as a
+ * stream of batches: the feed owns `nbuf` device staging batches of `batch` fields each (layout `order`: SITE, or a QUDA
+ * native order that is converted per batch); a producer fills batch b+1 on ITS stream while the loop kernels consume
+ * batch b on the feed's compute stream.
+ *   create    : `stream` is the compute stream; accumulate != 0: the first batch adds to dataPos_d instead of overwriting
+ *   acquire   : n <= batch device field pointers of the next staging batch; `producer_stream` is made to wait until the
+ *               kernels that last read that batch have finished (stream-ordered, the host does not block)
+ *   commit    : the producer's writes on `producer_stream` are complete in stream order; enqueues (conversion +) the plan's
+ *               kernels for these n eigenvectors on the compute stream
+ *   push_host : acquire + cudaMemcpyAsync from (pinned) host fields on the feed's copy stream + commit, batch by batch:
+ *               the H2D copies of batch b+1 overlap the kernels of batch b; consecutive host fields travel as one copy
+ *   set_plan  : between runs, point the feed at another plan (e.g. rebuilt for a new gauge field) / loop buffer of the same
+ *               lattice and precision; the staging batches are kept
+ *   finish    : returns the number of eigenvectors consumed and re-arms the feed; work enqueued on the compute stream
+ *               afterwards (loop_plan_finalize, the cross-rank sum, the projection) sees the complete sum */
+typedef struct mugiq_b200_loop_feed_s mugiq_b200_loop_feed_t;
+int mugiq_b200_loop_feed_create(mugiq_b200_loop_feed_t **feed, const mugiq_b200_loop_plan_t *plan, void *dataPos_d, int batch,
+                                int nbuf, int order, int accumulate, void *stream);
+int mugiq_b200_loop_feed_destroy(mugiq_b200_loop_feed_t *feed);
+int mugiq_b200_loop_feed_set_plan(mugiq_b200_loop_feed_t *feed, const mugiq_b200_loop_plan_t *plan, void *dataPos_d);
+int mugiq_b200_loop_feed_acquire(mugiq_b200_loop_feed_t *feed, void **field_d, int n, void *producer_stream);
+int mugiq_b200_loop_feed_commit(mugiq_b200_loop_feed_t *feed, const double *sigma_h, int n, void *producer_stream);
+int mugiq_b200_loop_feed_push_host(mugiq_b200_loop_feed_t *feed, const void *const *evec_h, const double *sigma_h, int n);
+int mugiq_b200_loop_feed_finish(mugiq_b200_loop_feed_t *feed, long long *nvec_total);
+
 /* ---- stage 3: gamma-basis / time-slice reorder -------------------------------------------------- */
 /* out[t + Lt*((15-G) + 16*iL) + Lt*nData*v3] = sign[G] * in[x_eo + V4*(G + 16*iL)].
  * Replaces convertIdxOrder_mapGamma (lib/contract_wrappers.cu:133-156,

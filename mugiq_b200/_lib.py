@@ -68,6 +68,13 @@ SYMBOLS = {
     "mugiq_b200_halo_push_t": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "mugiq_b200_fused_tiling_check": (_i, [_pe, _i, _pg, _i, _i, _i, C.POINTER(_ll)]),
     "mugiq_b200_loop_plan_computed_slots": (_i, [_vp, _pi, _i]),
+    "mugiq_b200_loop_feed_create": (_i, [C.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mugiq_b200_loop_feed_destroy": (_i, [_vp]),
+    "mugiq_b200_loop_feed_set_plan": (_i, [_vp, _vp, _vp]),
+    "mugiq_b200_loop_feed_acquire": (_i, [_vp, _pvp, _i, _vp]),
+    "mugiq_b200_loop_feed_commit": (_i, [_vp, _pd, _i, _vp]),
+    "mugiq_b200_loop_feed_push_host": (_i, [_vp, _pvp, _pd, _i]),
+    "mugiq_b200_loop_feed_finish": (_i, [_vp, C.POINTER(_ll)]),
     "mugiq_b200_comm_unique_id": (_i, [_vp]),
     "mugiq_b200_comm_create": (_i, [C.POINTER(_vp), _vp, _i, _i]),
     "mugiq_b200_comm_destroy": (_i, [_vp]),

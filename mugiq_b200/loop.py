@@ -388,36 +388,20 @@ class Loop_Mugiq:
         return self._plan
 
     def _accumulate_from_host(self, plan):
-        """Eigenvectors resident in (pinned) HOST memory: double-buffered H2D copies of eigenvector batches on a
-        copy stream overlap the loop kernels of the previous batch."""
+        """Eigenvectors resident in (pinned) HOST memory: the library's streamed feed (mugiq_b200_loop_feed_*) moves them
+        batch by batch into a ring of device staging batches on its copy stream - consecutive host fields as ONE copy -
+        while the loop kernels of the previous batch run; what the reference does per eigenvector with
+        `*fineEvecL = *eVecs[n]` / prolongateEvec (lib/loop_mugiq.cpp:478-483)."""
         es = self.eigsolve
         nb = max(1, min(self.stream_batch, es.nEv))
-        vol = self.lat.volume
-        stage = [torch.empty((nb, vol, 12), dtype=self.dtype, device=self.device) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=self.device)
-        main = torch.cuda.current_stream()
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-        batches = [(b0, min(es.nEv, b0 + nb)) for b0 in range(0, es.nEv, nb)]
-
-        def issue(i):
-            b0, b1 = batches[i]
-            s = i & 1
-            with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(freed[s])
-                for k, n in enumerate(range(b0, b1)):
-                    stage[s][k].copy_(es.eVecs[n].reshape(vol, 12), non_blocking=True)
-                ready[s].record(copy_stream)
-
-        issue(0)
-        for i, (b0, b1) in enumerate(batches):
-            if i + 1 < len(batches):
-                issue(i + 1)
-            s = i & 1
-            main.wait_event(ready[s])
-            plan.accumulate(self.dataPos_d, [stage[s][k] for k in range(b1 - b0)], es.eVals_sigma[b0:b1], accumulate=i > 0)
-            freed[s].record(main)
+        if getattr(self, "_feed", None) is None or self._feed.batch != nb:
+            if getattr(self, "_feed", None) is not None:
+                self._feed.close()
+            self._feed = ops.LoopFeed(plan, self.dataPos_d, batch=nb, nbuf=2)
+        elif self._feed.plan is not plan or self._feed.dataPos is not self.dataPos_d:
+            self._feed.set_plan(plan, self.dataPos_d)   # the plan was rebuilt for a new gauge field
+        self._feed.push_host(es.eVecs, es.eVals_sigma)
+        self._feed.finish()
 
     # -- lib/loop_mugiq.cpp:323-434 ---------------------------------------------------------------------
     def performMomentumProjection(self):

@@ -288,6 +288,66 @@ class LoopPlan:
             pass
 
 
+class LoopFeed:
+    """mugiq_b200_loop_feed_*: streamed eigenvector feed of a LoopPlan (device staging ring, producer / consumer streams)."""
+
+    def __init__(self, plan, dataPos, batch=16, nbuf=2, order=0, accumulate=False):
+        _dev(dataPos)
+        self.plan, self.dataPos, self.batch = plan, dataPos, int(batch)
+        self._h = C.c_void_p()
+        with torch.cuda.device(dataPos.device):
+            check(_lib.load().mugiq_b200_loop_feed_create(C.byref(self._h), plan._h, dataPos.data_ptr(), int(batch), int(nbuf),
+                                                          int(order), int(bool(accumulate)), _stream()))
+
+    def set_plan(self, plan, dataPos):
+        """Point the feed at another plan / loop buffer of the same lattice (between runs); the staging ring is kept."""
+        _dev(dataPos)
+        check(_lib.load().mugiq_b200_loop_feed_set_plan(self._h, plan._h, dataPos.data_ptr()))
+        self.plan, self.dataPos = plan, dataPos
+
+    def push_host(self, evecs_h, sigma):
+        """Host (pinned) eigenvector tensors -> staging batches (H2D on the feed's copy stream) -> loop kernels."""
+        n = len(evecs_h)
+        for v in evecs_h:
+            if v.is_cuda or not v.is_contiguous():
+                raise RuntimeError("LoopFeed.push_host takes contiguous host tensors")
+        sig = (C.c_double * n)(*[float(s) for s in sigma])
+        with torch.cuda.device(self.dataPos.device):
+            check(_lib.load().mugiq_b200_loop_feed_push_host(self._h, ptr_array([v.data_ptr() for v in evecs_h]), sig, n))
+
+    def acquire(self, n, producer_stream=None):
+        """n device field pointers of the next staging batch, for a device-side producer working on `producer_stream`."""
+        arr = (C.c_void_p * n)()
+        st = C.c_void_p((producer_stream or torch.cuda.current_stream()).cuda_stream)
+        with torch.cuda.device(self.dataPos.device):
+            check(_lib.load().mugiq_b200_loop_feed_acquire(self._h, arr, int(n), st))
+        return [int(p) for p in arr]
+
+    def commit(self, sigma, producer_stream=None):
+        n = len(sigma)
+        sig = (C.c_double * n)(*[float(s) for s in sigma])
+        st = C.c_void_p((producer_stream or torch.cuda.current_stream()).cuda_stream)
+        with torch.cuda.device(self.dataPos.device):
+            check(_lib.load().mugiq_b200_loop_feed_commit(self._h, sig, n, st))
+
+    def finish(self):
+        n = C.c_longlong()
+        check(_lib.load().mugiq_b200_loop_feed_finish(self._h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self._h:
+            with torch.cuda.device(self.dataPos.device):
+                _lib.load().mugiq_b200_loop_feed_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def reorder_mapgamma(out, inp, nData, nLoop, L):
     _dev(out, inp)
     geom = make_geom(L, _prec(inp))
