@@ -652,8 +652,8 @@ def leg_e2e_cpp(h, wl, name):
     if not os.path.exists(exe):
         return {"unavailable": "mugiq_b200/host/build/loop_driver not built"}
     L = wl["L"]
-    cmd = [exe, "--bench", "--dim", *[str(x) for x in L], "--nev", str(h.args.nev or wl["nev"]), "--bench-steps", "3",
-           "--device", str(h.local_rank)]
+    cmd = [exe, "--bench", "--dim", *[str(x) for x in L], "--n-ev", str(h.args.nev or wl["nev"]), "--bench-steps", "3",
+           "--bench-batch", str(h.args.stream_batch), "--device", str(h.local_rank)]
     if wl["entries"]:
         cmd += ["--displace-entry-string", wl["entries"]]
     cmd += ["--bench-p2max", str(wl["p2max"])]

@@ -35,6 +35,7 @@ template <typename F, QudaFieldOrder order> class Displace {
   mugiq_b200_loop_plan_t *plan = nullptr;  // owned
 
   cudaGaugeField *createCudaGaugeField();
+  void reloadGauge();  // H2D of the (borrowed) host links into the existing device field
   void setupDisplacement(std::string dStr);
   DisplaceFlag WhichDisplaceFlag();
   DisplaceDir WhichDisplaceDir();

@@ -34,6 +34,9 @@ template <typename Float, QudaFieldOrder fieldOrder> class Loop_Mugiq {
   void *momWorkspace_d = nullptr;
   bool fusedMomProj = true;                 // stages 3+4 as one kernel on dataPos_d (no dataPosMP_d)
   void *evecStage_d = nullptr;  // site-major staging for QUDA-native eigenvectors
+  mugiq_b200_loop_feed_t *feed = nullptr;  // streamed eigenvectors (Eigsolve_Mugiq::setEvecProducer): device staging ring
+  int feedBatch = 0;
+  void *producerStream = nullptr;          // cudaStream_t the producer enqueues on
   const void *gaugeHost[4] = {nullptr, nullptr, nullptr, nullptr};  // borrowed (MugiqLoopParam::gauge): the T split cuts its slab
 
   const size_t SizeCplxFloat = sizeof(complex<Float>);
@@ -60,6 +63,7 @@ public:
   ~Loop_Mugiq();
   void writeLoopsHDF5();
   void computeCoarseLoop();
+  void resetRun();  // re-upload the host links and re-arm the projection for another computeCoarseLoop on this object
 
   // read access for callers and tests (the reference keeps the buffers private and only writes them to HDF5)
   const complex<Float> *hostDataPos() const { return dataPos; }

@@ -61,6 +61,10 @@ template <typename F, QudaFieldOrder order> cudaGaugeField *Displace<F, order>::
   return g;
 }
 
+template <typename F, QudaFieldOrder order> void Displace<F, order>::reloadGauge() {
+  MUGIQ_CHECK(mugiq_b200_gauge_upload(gaugeField->Gauge_p(), gaugePtr, &geom, nullptr));
+}
+
 template <typename F, QudaFieldOrder order> void Displace<F, order>::createLoopPlan(const std::vector<mugiq_b200_disp_entry_t> &entries) {
   if (plan) {
     mugiq_b200_loop_plan_destroy(plan);

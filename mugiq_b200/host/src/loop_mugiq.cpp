@@ -110,12 +110,21 @@ Loop_Mugiq<Float, fieldOrder>::Loop_Mugiq(MugiqLoopParam *loopParams_, Eigsolve_
 }
 
 template <typename Float, QudaFieldOrder fieldOrder> Loop_Mugiq<Float, fieldOrder>::~Loop_Mugiq() {
+  if (feed) mugiq_b200_loop_feed_destroy(feed);
+  if (producerStream) cudaStreamDestroy((cudaStream_t)producerStream);
   freeDataMemory();
   if (displace) delete displace;
   if (cPrm) delete cPrm;
 }
 
 template <typename Float, QudaFieldOrder fieldOrder> int Loop_Mugiq<Float, fieldOrder>::nLoop() const { return cPrm->nLoop; }
+
+// A second run on the same object (the reference builds one Loop_Mugiq per computeLoop call, lib/interface_mugiq.cpp:158-172):
+// the host links are uploaded again (they may have changed) and the call-once guard of the projection is re-armed.
+template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::resetRun() {
+  if (displace) displace->reloadGauge();
+  MomProjDone = MUGIQ_BOOL_FALSE;
+}
 
 template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::setupComms() {
   // one rank: it is its own "space" and "time" communicator
@@ -209,7 +218,8 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
 // The eigenvector x displacement loop nest (lib/loop_mugiq.cpp:440-525).
 template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::computeCoarseLoop() {
   const int nEv = eigsolve->eigParams->nEv;
-  if (nEv < 1 || nEv > (int)eigsolve->eVecs.size()) errorQuda("%s: nEv = %d but %zu eigenvectors were given", __func__, nEv, eigsolve->eVecs.size());
+  if (nEv < 1 || (!eigsolve->producer && nEv > (int)eigsolve->eVecs.size()))
+    errorQuda("%s: nEv = %d but %zu eigenvectors were given", __func__, nEv, eigsolve->eVecs.size());
   if (!eigsolve->eVals_sigma || (int)eigsolve->eVals_sigma->size() < nEv)
     errorQuda("%s: singular values are only defined for MdagM / MMdag eigensolves and are required here", __func__);
   const QudaPrecision evecPrec = eigsolve->eVecs[0]->Precision();
@@ -235,11 +245,53 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   }
   if (mugiq_b200_loop_plan_nloop(plan) != cPrm->nLoop) errorQuda("%s: plan holds %d loops, expected %d", __func__, mugiq_b200_loop_plan_nloop(plan), cPrm->nLoop);
 
+  const bool sharded = getLoopComm() && mugiqCommSize(getLoopComm()) > 1;
+  const size_t fieldBytes = eigsolve->eVecs[0]->Bytes();
+  const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
+  if (eigsolve->producer) {
+    // Streamed eigenvectors (the reference's prolongateEvec / field copy per eigenvector, lib/loop_mugiq.cpp:478-483,
+    // batched): the library's feed hands out device staging batches, the producer fills batch b+1 on its stream while
+    // the loop kernels consume batch b.
+    const int batch = std::max(1, std::min({eigsolve->producerBatch, nEv, 256}));
+    if (!feed || feedBatch != batch) {
+      if (feed) mugiq_b200_loop_feed_destroy(feed);
+      MUGIQ_CHECK(mugiq_b200_loop_feed_create(&feed, plan, dataPos_d, batch, 2, native ? abi_order(fieldOrder) : MUGIQ_B200_ORDER_SITE, 0, nullptr));
+      feedBatch = batch;
+    } else {
+      MUGIQ_CHECK(mugiq_b200_loop_feed_set_plan(feed, plan, dataPos_d));
+    }
+    if (!producerStream) HOST_CUDA(cudaStreamCreateWithFlags((cudaStream_t *)&producerStream, cudaStreamNonBlocking));
+    std::vector<void *> slot(batch);
+    std::vector<double> sigma(batch);
+    ColorSpinorParam cs;
+    for (int i = 0; i < 4; i++) cs.x[i] = cPrm->localL[i];
+    cs.precision = precision_of<Float>();
+    cs.fieldOrder = fieldOrder;
+    for (int n0 = 0; n0 < nEv; n0 += batch) {
+      const int nb = std::min(batch, nEv - n0);
+      MUGIQ_CHECK(mugiq_b200_loop_feed_acquire(feed, slot.data(), nb, producerStream));
+      for (int i = 0; i < nb; i++) {
+        cs.v = slot[i];  // wraps the staging field, not owned
+        ColorSpinorField fine(cs);
+        eigsolve->producer(eigsolve->producerCtx, n0 + i, &fine, producerStream);
+        sigma[i] = (double)(Float)(*(eigsolve->eVals_sigma))[n0 + i];
+      }
+      MUGIQ_CHECK(mugiq_b200_loop_feed_commit(feed, sigma.data(), nb, producerStream));
+      printfQuda("%s: Loop trace for eigenvectors %04d - %04d enqueued\n", __func__, n0, n0 + nb - 1);
+    }
+    long long fed = 0;
+    MUGIQ_CHECK(mugiq_b200_loop_feed_finish(feed, &fed));
+    if (fed != nEv) errorQuda("%s: the feed consumed %lld of %d eigenvectors", __func__, fed, nEv);
+    if (sharded) {  // sum of the slots the plan computed, after the last batch
+      std::vector<int> slots(cPrm->nLoop);
+      const int ns = mugiq_b200_loop_plan_computed_slots(plan, slots.data(), cPrm->nLoop);
+      if (ns < 1) errorQuda("%s: %s", __func__, mugiq_b200_last_error());
+      MUGIQ_CHECK(mugiq_b200_allreduce_pos(dataPos_d, slots.data(), ns, 0, -1, &geom, mugiqCommHandle(getLoopComm()), nullptr));
+    }
+  } else {
   // eigenvectors are consumed in batches; QUDA-native orders are converted to the site-major layout batch by batch
   // Every batch costs one read-modify-write of the computed loop slots, so batches are as large as the kernel's
   // pointer table allows (256); QUDA-native fields need a site-major staging copy, which is capped at 4 GiB.
-  const size_t fieldBytes = eigsolve->eVecs[0]->Bytes();
-  const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
   int batch = 256;
   if (native) batch = (int)std::max<size_t>(8, std::min<size_t>(256, ((size_t)4 << 30) / fieldBytes));
   batch = std::min(batch, nEv);
@@ -247,7 +299,6 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   std::vector<const void *> ptr(batch), src(batch);
   std::vector<void *> stage(batch);
   std::vector<double> sigma(batch);
-  const bool sharded = getLoopComm() && mugiqCommSize(getLoopComm()) > 1;
   for (int n0 = 0; n0 < nEv; n0 += batch) {
     const int nb = std::min(batch, nEv - n0);
     for (int i = 0; i < nb; i++) {
@@ -268,6 +319,7 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
     else
       MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0, nullptr));
     printfQuda("%s: Loop trace for eigenvectors %04d - %04d completed\n", __func__, n0, n0 + nb - 1);
+  }
   }
   if (sharded) printfQuda("%s: Loop buffer summed over %d ranks\n", __func__, mugiqCommSize(getLoopComm()));
   // slots derived from computed ones (minus-direction partners, repeated entries) are linear in them: filled after the sum

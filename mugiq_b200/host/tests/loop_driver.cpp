@@ -7,9 +7,16 @@
 //               --momenta-filename mom.txt --loop-ft-sign minus --loop-write-mom-space yes
 //               --loop-mom-space-filename loops.dat [--field-order site|float2|float4] [--dump-pos f] [--dump-mom f]
 //   loop_driver --parse-only ...   parses and prints the loop parameters, touches no GPU (used by the CPU tests)
+//   loop_driver --bench --dim 16 16 16 32 --n-ev 200 --displace-entry-string "+x:1;..." --bench-p2max 1 --bench-steps 3
+//               end-to-end timing of the C++ front end on synthetic data: eigenvectors in PINNED HOST memory streamed
+//               through Eigsolve_Mugiq::setEvecProducer (H2D inside the timed region), links uploaded every step, dataPos
+//               and dataMom copied back; prints one JSON line with the fields of bench.py's `e2e` object
 // File formats: evecs [nEv][V4 (even/odd order)][12] complex, gauge [4][V4][3][3] complex, sigma nEv doubles.
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <complex>
+#include <cstdint>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -42,6 +49,16 @@ template <typename Float> static void to_native(std::vector<char> &field, QudaFi
       for (int k = 0; k < 24; k++)
         dst[pty * volumeCB * 24 + ((size_t)(k / N) * volumeCB + x) * N + k % N] = src[(pty * volumeCB + x) * 24 + k];
   field.swap(out);
+}
+
+// ---- eigenvectors that live in host memory: producer for Eigsolve_Mugiq::setEvecProducer -------------------------
+struct HostEvecs {
+  const char *base;
+  size_t fieldBytes;
+};
+static void copy_from_host(void *ctx, int n, ColorSpinorField *fine, void *stream) {
+  const HostEvecs *h = static_cast<const HostEvecs *>(ctx);
+  HOST_CUDA(cudaMemcpyAsync(fine->V(), h->base + (size_t)n * h->fieldBytes, h->fieldBytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
 }
 
 template <typename Float> static int run(std::map<std::string, std::string> &opt, const int Xg[4], MugiqLoopParam &prm, int nEv,
@@ -88,7 +105,11 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
     std::vector<double> shard(sigma.begin() + lo, sigma.begin() + hi);
     sigma.swap(shard);
   }
+  // --stream-evecs yes: the eigenvectors stay in HOST memory and reach the loop through the producer hook
+  // (Eigsolve_Mugiq::setEvecProducer, the stand-in for prolongateEvec): one device field only, as geometry reference
+  const bool streamEvecs = opt.count("--stream-evecs") && yes(opt["--stream-evecs"]);
   std::vector<ColorSpinorField *> fields;
+  std::vector<char> hostFields;
   ColorSpinorParam cs;
   for (int i = 0; i < 4; i++) cs.x[i] = X[i];
   cs.precision = prec;
@@ -105,6 +126,11 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
       one.assign(ev.begin() + n * fieldBytes, ev.begin() + (n + 1) * fieldBytes);
     }
     to_native<Float>(one, order, V4 / 2);
+    if (streamEvecs) {
+      hostFields.insert(hostFields.end(), one.begin(), one.end());
+      if (fields.empty()) fields.push_back(ColorSpinorField::Create(cs));
+      continue;
+    }
     fields.push_back(ColorSpinorField::Create(cs));
     HOST_CUDA(cudaMemcpy(fields.back()->V(), one.data(), fieldBytes, cudaMemcpyHostToDevice));
   }
@@ -112,6 +138,11 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
   qe.nEv = hi - lo;
   MugiqEigParam ep(&qe);
   Eigsolve_Mugiq eigsolve(&ep, fields, sigma);
+  HostEvecs he{hostFields.data(), fieldBytes};
+  if (streamEvecs) {
+    if (tsN > 0) errorQuda("--stream-evecs is not available with --tsplit");
+    eigsolve.setEvecProducer(copy_from_host, &he, opt.count("--stream-batch") ? atoi(opt["--stream-batch"].c_str()) : 4);
+  }
 
   if (opt.count("--dump-pos") || opt.count("--dump-mom")) {
     // class-level use (what computeLoop<Float,order> does), keeping the object to read its buffers
@@ -136,14 +167,123 @@ template <typename Float> static int run(std::map<std::string, std::string> &opt
   return 0;
 }
 
+// ---- --bench -----------------------------------------------------------------------------------------------------------
+static int run_bench(std::map<std::string, std::string> &opt, const int X[4], MugiqLoopParam &prm, int nEv) {
+  typedef double Float;
+  const size_t V4 = (size_t)X[0] * X[1] * X[2] * X[3];
+  const size_t fieldBytes = V4 * 24 * sizeof(Float);
+  const int steps = opt.count("--bench-steps") ? atoi(opt["--bench-steps"].c_str()) : 3;
+  const int batch = opt.count("--bench-batch") ? atoi(opt["--bench-batch"].c_str()) : 16;
+  const int p2max = opt.count("--bench-p2max") ? atoi(opt["--bench-p2max"].c_str()) : 0;
+  // momenta |p|^2 <= p2max in lexicographic order (bench.py: momenta_up_to)
+  prm.momMatrix.clear();
+  const int pm = (int)std::ceil(std::sqrt((double)p2max));
+  for (int px = -pm; px <= pm; px++)
+    for (int py = -pm; py <= pm; py++)
+      for (int pz = -pm; pz <= pm; pz++)
+        if (px * px + py * py + pz * pz <= p2max) prm.momMatrix.push_back({px, py, pz});
+  prm.Nmom = (int)prm.momMatrix.size();
+  prm.doMomProj = MUGIQ_BOOL_TRUE;
+  prm.FTSign = LOOP_FT_SIGN_MINUS;
+  // synthetic inputs: eigenvectors in pinned host memory (unit norm), links in pageable host memory
+  char *ev_h = nullptr;
+  HOST_CUDA(cudaMallocHost((void **)&ev_h, fieldBytes * nEv));
+  std::vector<double> sigma(nEv);
+  double sumInvSigma = 0;
+  {
+    uint64_t s = 0x6d75676971ULL;
+    auto rnd = [&s]() {
+      s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+      return (double)((s >> 11) & ((1ULL << 53) - 1)) / (double)(1ULL << 53) - 0.5;
+    };
+    for (int n = 0; n < nEv; n++) {
+      Float *v = reinterpret_cast<Float *>(ev_h + (size_t)n * fieldBytes);
+      double nrm = 0;
+      for (size_t i = 0; i < V4 * 24; i++) {
+        v[i] = rnd();
+        nrm += v[i] * v[i];
+      }
+      const double inv = 1.0 / std::sqrt(nrm);
+      for (size_t i = 0; i < V4 * 24; i++) v[i] *= inv;
+      sigma[n] = 0.01 + 0.001 * n;
+      sumInvSigma += 1.0 / sigma[n];
+    }
+  }
+  std::vector<Float> gauge;
+  QudaGaugeParam gp;
+  if (prm.doNonLocal) {
+    gauge.resize(4 * V4 * 18);
+    uint64_t s = 12345;
+    for (Float &x : gauge) {
+      s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+      x = (double)((s >> 11) & ((1ULL << 53) - 1)) / (double)(1ULL << 53) - 0.5;
+    }
+    for (int i = 0; i < 4; i++) {
+      gp.X[i] = X[i];
+      prm.gauge[i] = gauge.data() + (size_t)i * V4 * 18;
+    }
+    gp.cpu_prec = gp.cuda_prec = QUDA_DOUBLE_PRECISION;
+    gp.gauge_order = QUDA_QDP_GAUGE_ORDER;
+    prm.gauge_param = &gp;
+  }
+  ColorSpinorParam cs;
+  for (int i = 0; i < 4; i++) cs.x[i] = X[i];
+  cs.precision = QUDA_DOUBLE_PRECISION;
+  cs.fieldOrder = QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
+  std::vector<ColorSpinorField *> fields{ColorSpinorField::Create(cs)};  // the geometry reference (lib/loop_mugiq.cpp:42-43)
+  QudaEigParam qe;
+  qe.nEv = nEv;
+  MugiqEigParam ep(&qe);
+  Eigsolve_Mugiq eigsolve(&ep, fields, sigma);
+  HostEvecs he{ev_h, fieldBytes};
+  eigsolve.setEvecProducer(copy_from_host, &he, batch);
+  Loop_Mugiq<Float, QUDA_SPACE_SPIN_COLOR_FIELD_ORDER> loop(&prm, &eigsolve);
+  cudaEvent_t e0, e1;
+  HOST_CUDA(cudaEventCreate(&e0));
+  HOST_CUDA(cudaEventCreate(&e1));
+  auto step = [&]() {
+    loop.resetRun();           // H2D of the links
+    loop.computeCoarseLoop();  // H2D of every eigenvector (streamed), kernels, D2H of dataPos and dataMom
+  };
+  step();  // warm-up
+  HOST_CUDA(cudaDeviceSynchronize());
+  HOST_CUDA(cudaEventRecord(e0, nullptr));
+  for (int i = 0; i < steps; i++) step();
+  HOST_CUDA(cudaEventRecord(e1, nullptr));
+  HOST_CUDA(cudaDeviceSynchronize());
+  float ms = 0;
+  HOST_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= steps;
+  // checksum of the result: sum_x T_1(x) = sum_n |v_n|^2 / sigma_n
+  std::complex<double> tr = 0;
+  for (size_t x = 0; x < V4; x++) tr += loop.hostDataPos()[x];
+  const double chk = std::abs(tr - sumInvSigma) / sumInvSigma;
+  const double h2d = (double)fieldBytes * nEv + (prm.doNonLocal ? (double)gauge.size() * sizeof(Float) : 0.0);
+  const double d2h = (double)(loop.numElemPos() + loop.numElemMom()) * 2 * sizeof(Float);
+  const double units = (double)nEv * V4 * loop.nLoop();
+  printf("{\"value\": %.6e, \"unit\": \"eigvec*site*loop contractions/s (16 gamma each)\", \"ms_per_step\": %.4f, \"steps\": %d, "
+         "\"h2d_bytes_per_step\": %.0f, \"d2h_bytes_per_step\": %.0f, \"h2d_GBps\": %.2f, \"stream_batch\": %d, \"nLoop\": %d, \"Nmom\": %d, "
+         "\"checksum_rel_err\": %.3e, \"front_end\": \"C++ host mirror (Loop_Mugiq<double> + Eigsolve_Mugiq::setEvecProducer over "
+         "mugiq_b200_loop_feed_*), eigenvectors in pinned host memory\"}\n",
+         units / (ms * 1e-3), ms, steps, h2d, d2h, h2d / (ms * 1e-3) / 1e9, batch, loop.nLoop(), prm.Nmom, chk);
+  fflush(stdout);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  delete fields[0];
+  cudaFreeHost(ev_h);
+  return chk < 1e-10 ? 0 : 2;
+}
+
 int main(int argc, char **argv) {
   std::map<std::string, std::string> opt;
   int X[4] = {0, 0, 0, 0};
-  bool parseOnly = false;
+  bool parseOnly = false, bench = false;
   for (int i = 1; i < argc; i++) {
     const std::string a = argv[i];
     if (a == "--parse-only") {
       parseOnly = true;
+    } else if (a == "--bench") {
+      bench = true;
     } else if (a == "--dim") {
       if (i + 4 >= argc) errorQuda("--dim needs four extents");
       for (int d = 0; d < 4; d++) X[d] = atoi(argv[++i]);
@@ -156,6 +296,7 @@ int main(int argc, char **argv) {
   }
   if (opt.count("--verbosity") && opt["--verbosity"] == "verbose") setVerbosityQuda(QUDA_VERBOSE);
   MugiqLoopParam prm;
+  if (bench && opt.count("--displace-entry-string") && !opt["--displace-entry-string"].empty()) opt["--loop-do-nonlocal"] = "yes";
   if (opt.count("--loop-do-nonlocal") && yes(opt["--loop-do-nonlocal"])) parseDisplaceEntryString(prm, opt["--displace-entry-string"]);
   if (opt.count("--loop-do-momproj") && yes(opt["--loop-do-momproj"])) {
     if (!opt.count("--momenta-filename")) errorQuda("Got option '--loop-do-momproj yes' but option --momenta-filename is not set!\n");
@@ -180,6 +321,11 @@ int main(int argc, char **argv) {
   }
   const int nEv = opt.count("--n-ev") ? atoi(opt["--n-ev"].c_str()) : 0;
   if (nEv < 1) errorQuda("--n-ev must be positive");
+  if (bench) {
+    if (opt.count("--device")) HOST_CUDA(cudaSetDevice(atoi(opt["--device"].c_str())));
+    setVerbosityQuda(QUDA_SILENT);
+    return run_bench(opt, X, prm, nEv);
+  }
   QudaFieldOrder order = QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
   if (opt.count("--field-order")) {
     if (opt["--field-order"] == "float2") order = QUDA_FLOAT2_FIELD_ORDER;

@@ -243,3 +243,41 @@ def test_driver_public_entry_point_and_fatal_errors(driver, tmp_path):
     assert r.returncode != 0 and "Not supported yet" in r.stderr
     r = run(driver, *base, "--prec", "single")
     assert r.returncode != 0  # evecs file has double-precision size
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["site", "float2"])
+def test_driver_streamed_eigenvectors_match_oracle(driver, oracle, tmp_path, order):
+    """The producer hook of the C++ mirror (Eigsolve_Mugiq::setEvecProducer, standing in for prolongateEvec,
+    /root/reference/lib/loop_mugiq.cpp:276-319,482): eigenvectors stay in host memory and travel through the library's feed
+    (staging batches of 4 out of 7 eigenvectors) instead of living on the device."""
+    from oracle import numpy_check as npc
+    from mugiq_b200.params import momenta_up_to
+    L, nEv = (4, 4, 4, 8), 7
+    ev, U, sig = _inputs(tmp_path, L, nEv, "double")
+    mom = momenta_up_to(1)
+    (tmp_path / "mom.txt").write_text("".join(f"{p[0]} {p[1]} {p[2]}\n" for p in mom))
+    entries = [(2, 1, 1, 3), (0, 0, 2, 2), (3, 0, 1, 1), (3, 1, 1, 1)]
+    r = run(driver, "--dim", *L, "--n-ev", nEv, "--evecs-file", tmp_path / "ev.bin", "--sigma-file", tmp_path / "sig.bin",
+            "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string", "+z:1,3;-x:2;-t:1;+t:1",
+            "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--field-order", order, "--stream-evecs", "yes",
+            "--stream-batch", 4, "--dump-pos", tmp_path / "pos.bin", "--dump-mom", tmp_path / "mom.bin")
+    assert r.returncode == 0, r.stderr
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    assert rel_err(np.fromfile(tmp_path / "pos.bin", dtype=np.complex128).reshape(ref.shape), ref) < TOL_F64
+    ref_mom = npc.momentum_projection(ref, mom, -1, L)
+    assert rel_err(np.fromfile(tmp_path / "mom.bin", dtype=np.complex128).reshape(ref_mom.shape), ref_mom) < TOL_F64
+
+
+@pytest.mark.gpu
+def test_driver_bench_mode_prints_the_e2e_fields(driver):
+    """loop_driver --bench: end-to-end timing of the C++ front end on synthetic host data (what bench.py reports as
+    e2e_cpp); the run checks its own result (sum_x T_1 = sum 1/sigma) and exits non-zero if it is off."""
+    import json
+    r = run(driver, "--bench", "--dim", 8, 4, 4, 8, "--n-ev", 7, "--displace-entry-string", "+x:1;-x:1;-t:1,2", "--bench-p2max", 1,
+            "--bench-steps", 2, "--bench-batch", 3)
+    assert r.returncode == 0, r.stderr + r.stdout
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["steps"] == 2 and d["nLoop"] == 5 and d["Nmom"] == 7 and d["value"] > 0 and d["checksum_rel_err"] < 1e-10
+    assert d["h2d_bytes_per_step"] == 7 * 8 * 4 * 4 * 8 * 192 + 4 * 8 * 4 * 4 * 8 * 144
+    assert d["d2h_bytes_per_step"] == (5 * 16 * 8 * 4 * 4 * 8 + 16 * 7 * 8 * 5) * 16
