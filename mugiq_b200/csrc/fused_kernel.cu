@@ -36,7 +36,7 @@
 //    the eigenvector loop.
 //  * Bank conflicts: 192-B site stride means lanes reading the same component hit only two 16-B bank groups.
 //    Instead of padding (which would forbid multi-row bulk copies) each lane reads its site with the spin index
-//    rotated by k = (site_index/2) mod 4, i.e. it keeps spin (b+k) mod 4 in register slot b.  The 8 lanes of a
+//    rotated by k = (lane/2) mod 4, i.e. it keeps spin (b+k) mod 4 in register slot b.  The 8 lanes of a
 //    quarter-warp then touch 8 distinct bank groups (conflict-free 128-bit reads); the rotation only relabels
 //    M[be][al] and is undone once in the epilogue.
 #include <algorithm>
@@ -47,280 +47,10 @@
 #include <vector>
 
 #include "fused.cuh"
+#include "fused_stage.cuh"
 
 namespace mugiq_b200 {
 
-// ---- PTX helpers: mbarrier + bulk TMA -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-// ---- stage map of a tile: the merged intervals of checkerboard-index space one eigenvector stage holds ------------
-// shared by host (sizing) and device (thread 0 of every CTA builds its own)
-constexpr int kMaxIv = kFusedMaxIv;
-struct StageMap {
-  int n;         // merged intervals = bulk copies per stage
-  int sites;     // sites per stage
-  int overflow;  // more than kMaxIv intervals (the host checks this before launching)
-  int par[kMaxIv], lo[kMaxIv], hi[kMaxIv];  // interval [lo, hi) of checkerboard indices of parity par, sorted by (par, lo)
-  int soff[kMaxIv];                          // first site of the interval inside the stage
-  // the bulk copies, precomputed for the issuing lanes
-  int cp_soff[kMaxIv];    // byte offset inside the stage
-  int cp_goff16[kMaxIv];  // offset inside the eigenvector, in units of 16 B
-  int cp_bytes[kMaxIv];
-};
-
-__host__ __device__ inline int wrap(int a, int n) {
-  a %= n;
-  return a < 0 ? a + n : a;
-}
-
-// insert [lo, hi) into the sorted list of disjoint intervals m.lo/m.hi[0..m.n), merging what overlaps or adjoins
-__host__ __device__ inline void iv_insert(StageMap &m, int lo, int hi) {
-  if (lo >= hi) return;
-  int i = 0;
-  while (i < m.n && m.hi[i] < lo) i++;
-  if (i < m.n && m.lo[i] <= hi) {  // touches interval i: grow it, swallow the followers it reaches
-    if (lo < m.lo[i]) m.lo[i] = lo;
-    if (hi > m.hi[i]) m.hi[i] = hi;
-    int k = i + 1;
-    while (k < m.n && m.lo[k] <= m.hi[i]) {
-      if (m.hi[k] > m.hi[i]) m.hi[i] = m.hi[k];
-      k++;
-    }
-    if (k > i + 1) {
-      for (int d = i + 1, s = k; s < m.n; d++, s++) {
-        m.lo[d] = m.lo[s];
-        m.hi[d] = m.hi[s];
-      }
-      m.n -= k - (i + 1);
-    }
-    return;
-  }
-  if (2 * (m.n + 1) > kMaxIv) {  // the list is replicated for the second parity at the end
-    m.overflow = 1;
-    return;
-  }
-  for (int d = m.n; d > i; d--) {
-    m.lo[d] = m.lo[d - 1];
-    m.hi[d] = m.hi[d - 1];
-  }
-  m.lo[i] = lo;
-  m.hi[i] = hi;
-  m.n++;
-}
-
-// Stage of the run [c0, c1) (both parities) for the loops of grp: the run itself plus, per loop, the image of every row
-// piece of the run.  A y/z/t shift maps the piece [a, b) of row r to the same positions of the shifted row; an x shift
-// of length k keeps the row and moves the half-row index by at most ceil(k/2) (periodic inside the row).  Both
-// parities are staged for every image (a site's neighbour has parity p ^ (k & 1) and both own parities are in the tile),
-// so the interval list is built once and replicated.  Images of consecutive row pieces usually adjoin: they are joined
-// before they are inserted.
-__host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &grp, const LatGeom &g, int site_bytes, int c0,
-                                                int c1) {
-  m.n = 0;
-  m.overflow = 0;
-  const int Lh = g.Lh;
-  iv_insert(m, c0, c1);
-  for (int j = 0; j < grp.nloops; j++) {
-    const FusedLoop &lp = grp.loop[j];
-    const int sh = lp.sign * lp.len;
-    int plo = 0, phi = 0;  // pending image interval
-    for (int c = c0; c < c1;) {
-      const int row = c / Lh, a = c - row * Lh;
-      int b = a + (c1 - c);
-      if (b > Lh) b = Lh;
-      const int base = row * Lh;
-      int lo, hi;
-      if (lp.dir == 0) {
-        const int h = (lp.len + 1) >> 1;
-        lo = a - h;
-        hi = b + h;
-        if (hi - lo >= Lh) {
-          lo = 0;
-          hi = Lh;
-        }
-        if (lo < 0) {
-          iv_insert(m, base + lo + Lh, base + Lh);
-          lo = 0;
-        }
-        if (hi > Lh) {
-          iv_insert(m, base, base + hi - Lh);
-          hi = Lh;
-        }
-        lo += base;
-        hi += base;
-      } else {
-        int y = row % g.L[1], z = (row / g.L[1]) % g.L[2], t = row / (g.L[1] * g.L[2]);
-        if (lp.dir == 1) y = wrap(y + sh, g.L[1]);
-        if (lp.dir == 2) z = wrap(z + sh, g.L[2]);
-        if (lp.dir == 3) t = wrap(t + sh, g.L[3]);
-        const int nb = (y + g.L[1] * (z + g.L[2] * t)) * Lh;
-        lo = nb + a;
-        hi = nb + b;
-      }
-      if (lo <= phi && plo <= hi && phi > plo) {  // adjoins or overlaps the pending image: join
-        if (lo < plo) plo = lo;
-        if (hi > phi) phi = hi;
-      } else {
-        iv_insert(m, plo, phi);
-        plo = lo;
-        phi = hi;
-      }
-      c += b - a;
-    }
-    iv_insert(m, plo, phi);
-  }
-  // parity 0 block, then the same intervals for parity 1
-  const int n = m.n;
-  int off = 0;
-  for (int p = 0; p < 2; p++)
-    for (int i = 0; i < n; i++) {
-      const int k = p * n + i;
-      m.par[k] = p;
-      m.lo[k] = m.lo[i];
-      m.hi[k] = m.hi[i];
-      m.soff[k] = off;
-      m.cp_soff[k] = off * site_bytes;
-      m.cp_goff16[k] = (int)((((long long)p * g.volumeCB + m.lo[i]) * site_bytes) >> 4);
-      m.cp_bytes[k] = (m.hi[i] - m.lo[i]) * site_bytes;
-      off += m.hi[i] - m.lo[i];
-    }
-  m.n = 2 * n;
-  m.sites = off;
-}
-
-// position (in sites) of checkerboard site cb of parity par inside the stage; -1 if the stage does not hold it
-__host__ __device__ inline int stage_site(const StageMap &m, int par, int cb) {
-  const int n = m.n >> 1;
-  for (int i = par * n; i < (par + 1) * n; i++)
-    if (m.lo[i] <= cb && cb < m.hi[i]) return m.soff[i] + cb - m.lo[i];
-  return -1;
-}
-
-// checkerboard index of the site x + sign*len*dir a loop reads for the own site (parity p, checkerboard index cb);
-// its parity is p ^ (len & 1).  Neighbour selection of lib/mugiq_displace_kernels.cu:116-151 for a hop of `len` links.
-__host__ __device__ inline int neighbour_cb(const LatGeom &g, const FusedLoop &lp, int p, int cb) {
-  const int Lh = g.Lh;
-  const int row = cb / Lh, sx = cb - row * Lh;
-  const int ya = row % g.L[1], za = (row / g.L[1]) % g.L[2], ta = row / (g.L[1] * g.L[2]);
-  const int sh = lp.sign * lp.len;
-  if (lp.dir == 0) {
-    const int x = 2 * sx + ((ya + za + ta + p) & 1);
-    return row * Lh + (wrap(x + sh, g.L[0]) >> 1);
-  }
-  int yn = ya, zn = za, tn = ta;
-  if (lp.dir == 1) yn = wrap(ya + sh, g.L[1]);
-  if (lp.dir == 2) zn = wrap(za + sh, g.L[2]);
-  if (lp.dir == 3) tn = wrap(ta + sh, g.L[3]);
-  return (yn + g.L[1] * (zn + g.L[2] * tn)) * Lh + sx;
-}
-
-template <typename F> struct FusedArgs {
-  LatGeom g;
-  FusedTiling tl;
-  FusedGroup grp;      // displaced loops only (0..kFusedMaxLoops)
-  FusedVecTable vt;
-  F *dataPos;
-  long long ul_off;    // complex offset of the ultra-local loop's block in dataPos, < 0: not in this launch
-  int accumulate;
-  int c_begin, c_end;  // checkerboard-index range [c_begin, c_end) of both parities this launch computes: the time-slices
-                       // [t_begin, t_end) of a lattice-T split slab, or the whole lattice
-};
-
-constexpr int kSmemHeader = 3072;  // barriers + stage map
-
-template <typename F> __device__ __forceinline__ Cplx<F> lds_c(const char *p) {
-  using V = typename vec2_of<F>::type;
-  const V v = *reinterpret_cast<const V *>(p);
-  return make_c<F>(v.x, v.y);
-}
-
-// The ultra-local spin matrix M0 = sum_n (1/sigma_n) v_n(x)^dag (x) v_n(x) is Hermitian: 4 real diagonal
-// entries (index 0..3) and 6 complex entries be < al (index 4..9).  They are shared out among the threads
-// that work on the same site for the displaced loops of the group (balanced to +-1 entry), so that the
-// ultra-local loop costs no warp of its own.
-__host__ __device__ constexpr int ul_pair_be(int e) { return e < 7 ? 0 : (e < 9 ? 1 : 2); }
-__host__ __device__ constexpr int ul_pair_al(int e) { return e == 4 ? 1 : e == 5 ? 2 : e == 6 ? 3 : e == 7 ? 2 : 3; }
-__host__ __device__ constexpr int ul_pair_index(int be, int al) {  // be < al
-  return be == 0 ? 3 + al : be == 1 ? 5 + al : 9;
-}
-
-// rotate the first (kRow) or second index of a 4x4 matrix back: out[(b+K)&3][a] = in[b][a]
-template <typename F, int K, bool kRow> __device__ __forceinline__ void unrotate(Cplx<F> M[4][4]) {
-  Cplx<F> T[4][4];
-#pragma unroll
-  for (int b = 0; b < 4; b++)
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      if (kRow)
-        T[(b + K) & 3][a] = M[b][a];
-      else
-        T[b][(a + K) & 3] = M[b][a];
-    }
-#pragma unroll
-  for (int b = 0; b < 4; b++)
-#pragma unroll
-    for (int a = 0; a < 4; a++) M[b][a] = T[b][a];
-}
-template <typename F, bool kRow> __device__ __forceinline__ void unrotate_rt(Cplx<F> M[4][4], int k) {
-  if (k == 1) unrotate<F, 1, kRow>(M);
-  if (k == 2) unrotate<F, 2, kRow>(M);
-  if (k == 3) unrotate<F, 3, kRow>(M);
-}
-
-// Everything a thread needs inside the eigenvector loop.
-template <typename F> struct ThreadCtx {
-  const char *stages;
-  uint64_t *full, *empty;
-  const StageMap *st;
-  int S, stage_bytes, nvec, ahead, nActive, warp, lane;
-  int own_sp[4], nbr_sp[4];  // byte offsets (inside a stage) of the 4 rotated spin blocks of v(x) and v(x+d)
-};
-
-// Share of the ultra-local matrix a thread accumulates (compile-time: only the needed FMAs are issued).
-//   UL_NONE : nothing
-//   UL_ALL  : all 10 entries (groups with fewer than 4 displaced loops: role 0 does it alone)
-//   UL_ROT  : groups with 4 displaced loops.  Role j reads v(x) with its spin labels rotated by j on top of the
-//             bank rotation, and every role runs the SAME code: diagonal entry 0, pair (0,1), and - roles 0 and 1
-//             only - pair (0,2), in its own labels.  Over j = 0..3 that is d0..d3, the four "adjacent" pairs
-//             (0,1) (1,2) (2,3) (3,0) and the two "opposite" pairs (0,2) (1,3): all 10 entries exactly once,
-//             with one loop body in the instruction cache instead of four (no_instruction stalls were 12%).
-enum { UL_NONE = 0, UL_ALL = 1, UL_ROT = 2 };
-
-// ---- hot-loop primitives on 32-bit shared addresses.  On B200 every non-FP64 instruction costs FP64 issue slots
-// (tools/microbench.cu: one IMAD per DFMA drops the DFMA rate from 33.5 to 18.3 TFLOP/s at 8 warps per SM), so the loop
-// body avoids branches (predicated mbarrier / TMA instructions instead of `if (lane == 0)` blocks), address
-// arithmetic (running per-thread addresses, immediates for the colour offset) and integer division.
-__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, int pred) {
-  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(bar), "r"(pred) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_if(uint32_t bar, uint32_t bytes, int pred) {
-  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}" ::"r"(bar),
-               "r"(bytes), "r"(pred)
-               : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s_if(uint32_t dst, const void *src_gmem, uint32_t bytes, uint32_t bar, int pred) {
-  asm volatile(
-      "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
-      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}" ::"r"(dst),
-      "l"(src_gmem), "r"(bytes), "r"(bar), "r"(pred)
-      : "memory");
-}
 // The eigenvector loop of one role: ND displaced loops in the group, this thread works on one of them and on its
 // share of the ultra-local entries.
 template <typename F, int ND, int UL>
@@ -497,7 +227,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   const size_t x_eo = (size_t)p * g.volumeCB + (size_t)cb;
   const bool ul_rot = has_ul && ND == 4;  // see UL_ROT
   const int s_own = max(stage_site(st, p, cb), 0);
-  const int k_own = (((s_own >> 1) & 3) + (ul_rot ? j : 0)) & 3;  // spin-label rotation of v(x): bank rotation + role rotation
+  // Spin-label rotation against bank conflicts: the 8 lanes of a quarter-warp read 16 B each at a 192-byte site stride,
+  // i.e. bank group (12 s + 3 k + c) mod 8 for stage position s and rotation k; with k = (lane / 2) mod 4 the groups are
+  // distinct whenever the two lanes of a pair sit on stage positions of different parity - consecutive sites, also across
+  // the jump between two row pieces of a run (Lx/2 = 12, 24), where a position-based rotation collided.
+  const int k_bank = (lane >> 1) & 3;
+  const int k_own = (k_bank + (ul_rot ? j : 0)) & 3;  // bank rotation + role rotation of the ultra-local share
   int k_nbr = 0;
 
   ThreadCtx<F> c;
@@ -521,7 +256,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   if (ND > 0) {
     // neighbour x + sign*len*dir and its place in the stage
     const int s_nbr = max(stage_site(st, (p + lp.len) & 1, neighbour_cb(g, lp, p, cb)), 0);
-    k_nbr = (s_nbr >> 1) & 3;
+    k_nbr = k_bank;
     const int off = s_nbr * kSite;
 #pragma unroll
     for (int b = 0; b < 4; b++) c.nbr_sp[b] = off + ((b + k_nbr) & 3) * (kSite / 4);
@@ -632,7 +367,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
 }
 
 // ---- host side: tiling and launch ----------------------------------------------------------------------------
-static int smem_limit_bytes() {
+static int fused_smem_limit_bytes() {
   // the opt-in limit is a per-device attribute: one cached value per device ordinal (one process may drive several GPUs)
   static int limit[64];
   static bool known[64];
@@ -674,13 +409,13 @@ static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int
   return it->second.first;
 }
 
-// Run length: 8 warps = (loops of the group) x (warps per loop), a warp = 32 consecutive sites of one parity, so a group
-// of 3 or 4 displaced loops gets runs of 32 sites per parity, 2 loops 64, 1 loop or the ultra-local loop alone 128;
-// shorter if the shared-memory ring would otherwise have fewer than 3 stages.
-static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int smem_limit, int c_begin,
-                          int c_end) {
+// Run length: the CTA's warps = (roles: threads working on one site) x (warps per role), a warp = 32 consecutive sites of
+// one parity.  v1 (8 warps, one loop per thread): a group of 3 or 4 displaced loops gets runs of 32 sites per parity,
+// 2 loops 64, 1 loop or the ultra-local loop alone 128; shorter if the shared-memory ring would otherwise have fewer than
+// `want_stages` stages.  smem_avail: dynamic shared memory minus what is not ring (header, exchange buffer per unit).
+static bool fused_choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int c_begin, int c_end,
+                         int warps, int roles, int smem_avail, int smem_per_unit, int want_stages) {
   const int site = 24 * (int)prec_bytes(precision);
-  const int nrole = grp.nloops > 0 ? grp.nloops : 1;
   int max_stages = 8;
   if (const char *e = getenv("MUGIQ_B200_FUSED_STAGES")) {
     const int want = atoi(e);
@@ -688,7 +423,7 @@ static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom 
   }
   FusedTiling best;
   best.nstages = 0;
-  for (int units = (kFusedComputeWarps / nrole) & ~1; units >= 2; units -= 2) {
+  for (int units = (warps / roles) & ~1; units >= 2; units -= 2) {
     FusedTiling t;
     t.units = units;
     t.run = 16 * units;
@@ -696,13 +431,20 @@ static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom 
     const int sites = max_stage_sites(grp, g, t.run, c_begin, c_end, &overflow);
     if (overflow) continue;
     t.stage_bytes = (sites * site + 127) / 128 * 128;
-    t.nstages = std::min(max_stages, (smem_limit - kSmemHeader - t.units * 32 * 16 * (int)prec_bytes(precision)) / t.stage_bytes);
+    t.nstages = std::min(max_stages, (smem_avail - t.units * smem_per_unit) / t.stage_bytes);
     if (t.nstages > best.nstages) best = t;
-    if (best.nstages >= std::min(3, max_stages)) break;
+    if (best.nstages >= std::min(want_stages, max_stages)) break;
   }
   if (best.nstages < 2) return false;
   tl = best;
   return true;
+}
+
+static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int smem_limit, int c_begin,
+                          int c_end) {
+  const int nrole = grp.nloops > 0 ? grp.nloops : 1;
+  return fused_choose_tiling(tl, grp, g, precision, c_begin, c_end, kFusedComputeWarps, nrole, smem_limit - kSmemHeader,
+                             32 * 16 * (int)prec_bytes(precision), 3);
 }
 
 // Host-only self-check of the tiling (no GPU needed; exported as mugiq_b200_fused_tiling_check for the CPU tests): for
@@ -759,7 +501,7 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
       grp.loop[j].out_off = 0;
     }
     FusedTiling tl;
-    if (choose_tiling(tl, grp, g, precision, smem_limit_bytes(), 0, g.volumeCB)) return nl;
+    if (choose_tiling(tl, grp, g, precision, fused_smem_limit_bytes(), 0, g.volumeCB)) return nl;
   }
   return -1;
 }
@@ -771,7 +513,7 @@ template <typename F, int ND> static int launch_fused_nd(const FusedArgs<F> &arg
   MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem_limit_bytes()));
+                                          fused_smem_limit_bytes()));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   loop_fused_kernel<F, ND><<<grid, kFusedThreads, smem, stream>>>(args);
@@ -793,7 +535,7 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   const int V3h = g.V3 / 2;
   args.c_begin = t_begin * V3h;
   args.c_end = t_end * V3h;
-  if (!choose_tiling(args.tl, grp, g, precision, smem_limit_bytes(), args.c_begin, args.c_end))
+  if (!choose_tiling(args.tl, grp, g, precision, fused_smem_limit_bytes(), args.c_begin, args.c_end))
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
   const int grid = (args.c_end - args.c_begin + args.tl.run - 1) / args.tl.run;

@@ -13,7 +13,8 @@ using namespace quda;
 Eigsolve_Mugiq::Eigsolve_Mugiq(MugiqEigParam *eigParams_, const std::vector<ColorSpinorField *> &evecs, const std::vector<double> &sigma)
     : eigParams(eigParams_), eVecs(evecs), eVals_sigma(sigma.empty() ? nullptr : new std::vector<double>(sigma)) {
   if (!eigParams) errorQuda("Eigsolve_Mugiq: eigParams is NULL");
-  if (eigParams->nEv > (int)eVecs.size()) errorQuda("Eigsolve_Mugiq: nEv = %d but only %zu eigenvectors given", eigParams->nEv, eVecs.size());
+  // with a producer (setEvecProducer) one field suffices; Loop_Mugiq::computeCoarseLoop checks the count when it runs
+  if (eVecs.empty()) errorQuda("Eigsolve_Mugiq: no eigenvector field given (at least the geometry reference is needed)");
 }
 Eigsolve_Mugiq::~Eigsolve_Mugiq() { delete eVals_sigma; }
 void Eigsolve_Mugiq::printInfo() {
