@@ -198,6 +198,13 @@ int mugiq_b200_loop_plan_info(const mugiq_b200_loop_plan_t *plan, int *ncomputed
 /* The dataPos slots (iL) accumulate() writes - what a cross-rank sum has to cover; the others are filled by finalize().
  * Writes at most max_slots of them, returns how many there are. */
 int mugiq_b200_loop_plan_computed_slots(const mugiq_b200_loop_plan_t *plan, int *slots, int max_slots);
+/* Eigenvectors in QUDA's native FLOAT2 order ([parity][spin*3+colour][x_cb], what FieldOrderCB hands the reference's kernels,
+ * lib/mugiq_contract_kernels.cu:82-83; interface_mugiq.cpp:226-235 dispatches on it): after set_evec_order(plan,
+ * MUGIQ_B200_ORDER_FLOAT2) every accumulate form of the plan (accumulate, accumulate_allreduce, the feed) takes FLOAT2
+ * fields and the fused kernel stages them itself - each field is a 4-D tensor (8 sites, 12 components, volumeCB/8 chunks,
+ * 2 parities) and the pieces of a stage arrive as TMA tensor boxes - so no layout-conversion pass and no site-major copy
+ * exist.  Needs volumeCB % 8 == 0.  MUGIQ_B200_ORDER_SITE (default) restores the canonical order. */
+int mugiq_b200_loop_plan_set_evec_order(mugiq_b200_loop_plan_t *plan, int order);
 /* Lattice-T split (BASELINE config 5): a rank runs the plan on its time slab EXTENDED by halo slices.
  *   set_t_range : accumulate() computes dataPos only on the time-slices [t_begin, t_end) of the plan's lattice (the
  *                 rank's interior) and merely reads the others; finalize() still spans the whole lattice.
@@ -218,16 +225,17 @@ int mugiq_b200_loop_plan_finalize(const mugiq_b200_loop_plan_t *plan, void *data
  * site must lie in the merged intervals its CTA stages per eigenvector.  group < 0 returns the number of launch groups.
  * out = {run (checkerboard sites per parity and CTA), warps per loop, ring stages, stage bytes, most bulk copies per
  * stage, mean sites staged per CTA and eigenvector, sites NOT found in their stage (must be 0), malformed stage maps
- * (must be 0)}. */
+ * (must be 0)}.  evec_order: MUGIQ_B200_ORDER_SITE or _FLOAT2 (the tiling of natively ordered eigenvectors, see
+ * mugiq_b200_loop_plan_set_evec_order). */
 int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int nentries, const mugiq_b200_geom_t *geom,
-                                  int t_begin, int t_end, int group, long long out[8]);
+                                  int t_begin, int t_end, int group, int evec_order, long long out[8]);
 
 /* ---- streamed eigenvector feed of a loop plan --------------------------------------------------------------------- */
 /* The producer/consumer form of the eigenvector loop: the reference makes the fine eigenvector right before it is used,
  * `prolongateEvec(fineEvecL, eVecs[n])` through the multigrid transfer operators or a field copy (lib/loop_mugiq.cpp:276-319,
  * 478-483).  1000-2000 fine eigenvectors of the BASELINE lattices do not fit a GPU, so the fused path takes them as a
- * stream of batches: the feed owns `nbuf` device staging batches of `batch` fields each (layout `order`: SITE, or a QUDA
- * native order that is converted per batch); a producer fills batch b+1 on ITS stream while the loop kernels consume
+ * stream of batches: the feed owns `nbuf` device staging batches of `batch` fields each (layout `order`: SITE or FLOAT2,
+ * which the kernels stage directly, or FLOAT4, which is converted per batch); a producer fills batch b+1 on ITS stream while the loop kernels consume
  * batch b on the feed's compute stream.
  *   create    : `stream` is the compute stream; accumulate != 0: the first batch adds to dataPos_d instead of overwriting
  *   acquire   : n <= batch device field pointers of the next staging batch; `producer_stream` is made to wait until the

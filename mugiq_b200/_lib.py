@@ -66,7 +66,8 @@ SYMBOLS = {
     "mugiq_b200_peer_close": (_i, [_vp]),
     "mugiq_b200_peer_free": (_i, [_vp]),
     "mugiq_b200_halo_push_t": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _i, _i, _i, _vp]),
-    "mugiq_b200_fused_tiling_check": (_i, [_pe, _i, _pg, _i, _i, _i, C.POINTER(_ll)]),
+    "mugiq_b200_fused_tiling_check": (_i, [_pe, _i, _pg, _i, _i, _i, _i, C.POINTER(_ll)]),
+    "mugiq_b200_loop_plan_set_evec_order": (_i, [_vp, _i]),
     "mugiq_b200_loop_plan_computed_slots": (_i, [_vp, _pi, _i]),
     "mugiq_b200_loop_feed_create": (_i, [C.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _vp]),
     "mugiq_b200_loop_feed_destroy": (_i, [_vp]),

@@ -55,7 +55,9 @@ static int feed_commit(mugiq_b200_loop_feed_s *f, const double *sigma_h, int n, 
   MUGIQ_CUDA_CHECK(cudaStreamWaitEvent(f->compute, f->filled, 0));
   std::vector<const void *> ptr(n);
   int rc = MUGIQ_B200_OK;
-  if (f->order != MUGIQ_B200_ORDER_SITE) {  // producer's native order -> canonical site-major, one launch for the batch
+  // FLOAT2 staging batches go to the kernels as they are (tensor-box staging); FLOAT4 ones are converted first
+  const bool convert = f->site != nullptr;
+  if (convert) {  // producer's native order -> canonical site-major, one launch for the batch
     std::vector<void *> dst(n);
     std::vector<const void *> src(n);
     for (int i = 0; i < n; i++) {
@@ -70,9 +72,9 @@ static int feed_commit(mugiq_b200_loop_feed_s *f, const double *sigma_h, int n, 
     for (int i = 0; i < n; i++) ptr[i] = f->stage[b] + (size_t)i * f->field_bytes;
   }
   rc = plan_accumulate_range(*f->pl, f->dataPos_d, ptr.data(), sigma_h, n, f->accumulate0 || f->total > 0, f->pl->t_begin,
-                             f->pl->t_end, f->total == 0, f->compute);
+                             f->pl->t_end, f->total == 0, f->compute, convert ? MUGIQ_B200_ORDER_SITE : f->order);
   if (rc) return rc;
-  if (f->order == MUGIQ_B200_ORDER_SITE) MUGIQ_CUDA_CHECK(cudaEventRecord(f->freed[b], f->compute));
+  if (!convert) MUGIQ_CUDA_CHECK(cudaEventRecord(f->freed[b], f->compute));
   f->used[b] = true;
   f->total += n;
   f->next = (b + 1) % f->nbuf;
@@ -117,7 +119,8 @@ int mugiq_b200_loop_feed_create(mugiq_b200_loop_feed_t **feed, const mugiq_b200_
     }
     if (cudaEventCreateWithFlags(&f->freed[b], cudaEventDisableTiming) != cudaSuccess) return fail(MUGIQ_B200_ECUDA, "cudaEventCreate failed");
   }
-  if (order != MUGIQ_B200_ORDER_SITE && cudaMalloc((void **)&f->site, f->field_bytes * batch) != cudaSuccess) {
+  const bool direct = order == MUGIQ_B200_ORDER_SITE || (order == MUGIQ_B200_ORDER_FLOAT2 && f->pl->g.volumeCB % 8 == 0);
+  if (!direct && cudaMalloc((void **)&f->site, f->field_bytes * batch) != cudaSuccess) {
     cudaGetLastError();
     return fail(MUGIQ_B200_ENOMEM, "cannot allocate the conversion batch");
   }

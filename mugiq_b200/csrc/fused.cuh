@@ -38,9 +38,10 @@ struct FusedTiling {
 };
 
 struct FusedVecTable {
-  const void *evec[kFusedMaxVec];
+  const void *evec[kFusedMaxVec];  // site-major fields; native != 0: each eigenvector's tensor maps (fused_native_tmaps)
   double inv_sigma[kFusedMaxVec];
   int nvec;
+  int native;  // 0: canonical site-major fields; MUGIQ_B200_ORDER_FLOAT2: QUDA FLOAT2 fields staged as tensor boxes
 };
 
 // maximum number of displaced loops per group for this lattice / precision (warp and shared-memory budget)
@@ -52,7 +53,12 @@ int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off,
 
 // host-only self-check of the tiling of one launch group (fused_kernel.cu); out = {run, units, nstages, stage_bytes,
 // max copies per stage, mean sites staged per CTA, sites not found in their stage, malformed stage maps}
-int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, long long out[8]);
+int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, int native,
+                       long long out[8]);
+// device addresses of the tensor maps (three per eigenvector: boxes of 1, 2, 4 chunks of 8 sites) of QUDA FLOAT2 fields,
+// encoded on first use and cached per (address, lattice, precision); new entries are uploaded on `stream`
+int fused_native_tmaps(const void **tmap_d, const void *const *evec_d, int nvec, const LatGeom &g, int precision,
+                       cudaStream_t stream);
 
 // ---- gauge-only helpers (wilson.cu) ---------------------------------------------------------------------
 // Wout(x) = Win(x) * U_dir(x + shift*dir)       (extends a plus-direction Wilson line by one link)

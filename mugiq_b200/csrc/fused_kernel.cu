@@ -39,10 +39,13 @@
 //    rotated by k = (lane/2) mod 4, i.e. it keeps spin (b+k) mod 4 in register slot b.  The 8 lanes of a
 //    quarter-warp then touch 8 distinct bank groups (conflict-free 128-bit reads); the rotation only relabels
 //    M[be][al] and is undone once in the epilogue.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -53,7 +56,7 @@ namespace mugiq_b200 {
 
 // The eigenvector loop of one role: ND displaced loops in the group, this thread works on one of them and on its
 // share of the ultra-local entries.
-template <typename F, int ND, int UL>
+template <typename F, int ND, int UL, int NATIVE>
 __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx<F> &c, const Cplx<F> (&W)[3][3],
                                           Cplx<F> (&M)[4][4], F (&Md)[4], Cplx<F> (&Mo)[6], const bool opposite) {
   // producer side: the warps take turns - warp (m mod nActive) issues ALL bulk copies of eigenvector m's stage (lane i
@@ -61,12 +64,14 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
   // chip are paid in FP64 issue slots; spread over the warps in turn it is ~15 per warp and eigenvector instead of ~65
   // when every warp issued its own share every time.
   uint32_t total_tx = 0;
-  for (int i = 0; i < c.st->n; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
+  for (int i = 0; i < c.st->ncp; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
   const int lead = c.lane == 0;
   const uint32_t stages_u32 = smem_u32(c.stages);
   const uint32_t full_u32 = smem_u32(c.full), empty_u32 = smem_u32(c.empty);
   const int ring_bytes = c.S * c.stage_bytes;
-  constexpr int kC = 2 * (int)sizeof(F);
+  // distance between the colours of one spin: adjacent complex numbers (site-major), or component rows of a chunk of
+  // 8 sites (QUDA FLOAT2 stage, [chunk][component][8 sites])
+  constexpr int kC = NATIVE ? kChunk * 2 * (int)sizeof(F) : 2 * (int)sizeof(F);
 
   uint32_t p_full = full_u32, p_empty = empty_u32, p_dst = stages_u32;  // producer cursor (stage of the next issue)
   int p_left = c.S;                                                      // stages until the cursor wraps
@@ -77,9 +82,16 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
       if (wait) mbar_wait_u32(p_empty, p_par);
       const char *ev = static_cast<const char *>(A.vt.evec[m]);
       mbar_expect_tx_if(p_full, total_tx, lead);
-      for (int i = c.lane; i < c.st->n; i += 32)
-        tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4), (uint32_t)c.st->cp_bytes[i],
-                        p_full, 1);
+      if (NATIVE) {  // ev: this eigenvector's three tensor maps (boxes of 1, 2, 4 chunks) in device memory
+        for (int i = c.lane; i < c.st->ncp; i += 32) {
+          const int d = c.st->cp_goff16[i];
+          tma_tensor4_g2s(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((d >> 29) & 3) * 128, d & 0x0fffffff, (d >> 28) & 1, p_full);
+        }
+      } else {
+        for (int i = c.lane; i < c.st->ncp; i += 32)
+          tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4),
+                          (uint32_t)c.st->cp_bytes[i], p_full, 1);
+      }
       turn = c.nActive;
     }
     turn--;
@@ -184,7 +196,7 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
   }
 }
 
-template <typename F, int ND>
+template <typename F, int ND, int NATIVE>
 __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __grid_constant__ FusedArgs<F> A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);        // [nstages]
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   const int c1 = min(c0 + tl.run, A.c_end);
 
   if (threadIdx.x == 0) {
-    build_stage_map(st, A.grp, g, kSite, c0, c1);
+    build_stage_map(st, A.grp, g, kSite, c0, c1, NATIVE ? kChunk : 1);
     for (int s = 0; s < tl.nstages; s++) {
       mbar_init(&full[s], 1);        // one arrive.expect_tx by the warp whose turn it is
       mbar_init(&empty[s], nActive);
@@ -231,7 +243,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   // i.e. bank group (12 s + 3 k + c) mod 8 for stage position s and rotation k; with k = (lane / 2) mod 4 the groups are
   // distinct whenever the two lanes of a pair sit on stage positions of different parity - consecutive sites, also across
   // the jump between two row pieces of a run (Lx/2 = 12, 24), where a position-based rotation collided.
-  const int k_bank = (lane >> 1) & 3;
+  // A FLOAT2 stage needs none: consecutive sites are consecutive 16-byte words of a component row.
+  const int k_bank = NATIVE ? 0 : (lane >> 1) & 3;
   const int k_own = (k_bank + (ul_rot ? j : 0)) & 3;  // bank rotation + role rotation of the ultra-local share
   int k_nbr = 0;
 
@@ -247,19 +260,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   c.nActive = nActive;
   c.warp = warp;
   c.lane = lane;
+  constexpr int kSpin = NATIVE ? 3 * kChunk * 2 * (int)sizeof(F) : kSite / 4;  // distance between the spin blocks of a site
   {
-    const int off = s_own * kSite;
+    const int off = stage_site_bytes<NATIVE>(s_own, kSite);
 #pragma unroll
-    for (int b = 0; b < 4; b++) c.own_sp[b] = off + ((b + k_own) & 3) * (kSite / 4);
+    for (int b = 0; b < 4; b++) c.own_sp[b] = off + ((b + k_own) & 3) * kSpin;
   }
   const FusedLoop lp = A.grp.loop[ND > 0 ? j : 0];
   if (ND > 0) {
     // neighbour x + sign*len*dir and its place in the stage
     const int s_nbr = max(stage_site(st, (p + lp.len) & 1, neighbour_cb(g, lp, p, cb)), 0);
     k_nbr = k_bank;
-    const int off = s_nbr * kSite;
+    const int off = stage_site_bytes<NATIVE>(s_nbr, kSite);
 #pragma unroll
-    for (int b = 0; b < 4; b++) c.nbr_sp[b] = off + ((b + k_nbr) & 3) * (kSite / 4);
+    for (int b = 0; b < 4; b++) c.nbr_sp[b] = off + ((b + k_nbr) & 3) * kSpin;
   } else {
 #pragma unroll
     for (int b = 0; b < 4; b++) c.nbr_sp[b] = c.own_sp[b];
@@ -289,11 +303,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   const int ul_mode = !has_ul ? UL_NONE : (ND == 4 ? UL_ROT : (j == 0 ? UL_ALL : UL_NONE));
   if (active) {
     if (ul_mode == UL_NONE)
-      evec_loop<F, ND, UL_NONE>(A, c, W, M, Md, Mo, false);
+      evec_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo, false);
     else if (ul_mode == UL_ALL)
-      evec_loop<F, ND, UL_ALL>(A, c, W, M, Md, Mo, false);
+      evec_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo, false);
     else
-      evec_loop<F, ND, UL_ROT>(A, c, W, M, Md, Mo, j < 2);
+      evec_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo, j < 2);
   }
 
   // ---- epilogue: undo the spin rotation, gamma projection (adds/swaps only), one write of the loop buffer ---------
@@ -383,10 +397,10 @@ static int fused_smem_limit_bytes() {
 
 // Largest stage (in sites) over the CTAs of a launch, exact: the merged intervals of every run are evaluated once per
 // (lattice, group, run, range) and remembered - 10^4 runs of a few dozen interval insertions each.
-static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int c_begin, int c_end, bool *overflow) {
+static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int c_begin, int c_end, int align, bool *overflow) {
   static std::mutex mu;
   static std::map<std::vector<int>, std::pair<int, bool>> cache;
-  std::vector<int> key = {g.L[0], g.L[1], g.L[2], g.L[3], run, c_begin, c_end, grp.nloops};
+  std::vector<int> key = {g.L[0], g.L[1], g.L[2], g.L[3], run, c_begin, c_end, align, grp.nloops};
   for (int j = 0; j < grp.nloops; j++) {
     key.push_back(grp.loop[j].dir);
     key.push_back(grp.loop[j].sign);
@@ -399,7 +413,7 @@ static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int
     bool ovf = false;
     StageMap m;
     for (int c0 = c_begin; c0 < c_end; c0 += run) {
-      build_stage_map(m, grp, g, 1, c0, std::min(c0 + run, c_end));
+      build_stage_map(m, grp, g, 1, c0, std::min(c0 + run, c_end), align);
       best = std::max(best, m.sites);
       ovf = ovf || m.overflow;
     }
@@ -414,7 +428,7 @@ static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int
 // 2 loops 64, 1 loop or the ultra-local loop alone 128; shorter if the shared-memory ring would otherwise have fewer than
 // `want_stages` stages.  smem_avail: dynamic shared memory minus what is not ring (header, exchange buffer per unit).
 static bool fused_choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int c_begin, int c_end,
-                         int warps, int roles, int smem_avail, int smem_per_unit, int want_stages) {
+                                int warps, int roles, int smem_avail, int smem_per_unit, int want_stages, int align) {
   const int site = 24 * (int)prec_bytes(precision);
   int max_stages = 8;
   if (const char *e = getenv("MUGIQ_B200_FUSED_STAGES")) {
@@ -428,7 +442,7 @@ static bool fused_choose_tiling(FusedTiling &tl, const FusedGroup &grp, const La
     t.units = units;
     t.run = 16 * units;
     bool overflow = false;
-    const int sites = max_stage_sites(grp, g, t.run, c_begin, c_end, &overflow);
+    const int sites = max_stage_sites(grp, g, t.run, c_begin, c_end, align, &overflow);
     if (overflow) continue;
     t.stage_bytes = (sites * site + 127) / 128 * 128;
     t.nstages = std::min(max_stages, (smem_avail - t.units * smem_per_unit) / t.stage_bytes);
@@ -441,19 +455,22 @@ static bool fused_choose_tiling(FusedTiling &tl, const FusedGroup &grp, const La
 }
 
 static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int smem_limit, int c_begin,
-                          int c_end) {
+                          int c_end, int native = 0) {
   const int nrole = grp.nloops > 0 ? grp.nloops : 1;
   return fused_choose_tiling(tl, grp, g, precision, c_begin, c_end, kFusedComputeWarps, nrole, smem_limit - kSmemHeader,
-                             32 * 16 * (int)prec_bytes(precision), 3);
+                             32 * 16 * (int)prec_bytes(precision), 3, native ? kChunk : 1);
 }
 
 // Host-only self-check of the tiling (no GPU needed; exported as mugiq_b200_fused_tiling_check for the CPU tests): for
 // every CTA of a launch, the stage map must be sorted, disjoint and within the sized stage, and every thread's own and
 // neighbour site must lie in it.
-int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, long long out[8]) {
+int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, int native,
+                       long long out[8]) {
   FusedTiling tl;
   const int V3h = g.V3 / 2, c_begin = t_begin * V3h, c_end = t_end * V3h;
-  if (!choose_tiling(tl, grp, g, precision, 227 * 1024, c_begin, c_end))
+  if (native && g.volumeCB % kChunk)
+    return set_error(MUGIQ_B200_EINVAL, "fused_tiling_check: QUDA-ordered eigenvectors need volumeCB to be a multiple of %d", kChunk);
+  if (!choose_tiling(tl, grp, g, precision, 227 * 1024, c_begin, c_end, native))
     return set_error(MUGIQ_B200_EINVAL, "fused_tiling_check: no tiling fits");
   const int site = 24 * (int)prec_bytes(precision);
   long long misses = 0, bad_maps = 0, stage_sites = 0, ctas = 0;
@@ -461,10 +478,23 @@ int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, i
   StageMap m;
   for (int c0 = c_begin; c0 < c_end; c0 += tl.run) {
     const int c1 = std::min(c0 + tl.run, c_end);
-    build_stage_map(m, grp, g, site, c0, c1);
+    build_stage_map(m, grp, g, site, c0, c1, native ? kChunk : 1);
     ctas++;
     stage_sites += m.sites;
-    max_copies = std::max(max_copies, m.n);
+    max_copies = std::max(max_copies, m.ncp);
+    if (native) {  // copies: whole chunks, inside the stage and the lattice, covering every interval exactly once
+      long long covered = 0;
+      for (int i = 0; i < m.ncp; i++) {
+        const int d = m.cp_goff16[i], nb = 1 << ((d >> 29) & 3), chunk = d & 0x0fffffff;
+        if (m.cp_bytes[i] != nb * kChunk * site || (m.cp_soff[i] % (kChunk * site)) || (chunk + nb) * kChunk > g.volumeCB ||
+            m.cp_soff[i] + m.cp_bytes[i] > tl.stage_bytes)
+          bad_maps++;
+        covered += nb * kChunk;
+      }
+      if (covered != m.sites) bad_maps++;
+      for (int i = 0; i < m.n; i++)
+        if ((m.lo[i] % kChunk) || (m.hi[i] % kChunk)) bad_maps++;
+    }
     if (m.overflow || m.sites * site > tl.stage_bytes) bad_maps++;
     for (int i = 0; i + 1 < m.n; i++)
       if (m.par[i] > m.par[i + 1] || (m.par[i] == m.par[i + 1] && m.hi[i] >= m.lo[i + 1])) bad_maps++;
@@ -506,17 +536,18 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
   return -1;
 }
 
-template <typename F, int ND> static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
+template <typename F, int ND, int NATIVE>
+static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
   // the shared-memory opt-in is a per-device function attribute
   static bool attr_set[64];
   int dev = 0;
   MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND, NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           fused_smem_limit_bytes()));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  loop_fused_kernel<F, ND><<<grid, kFusedThreads, smem, stream>>>(args);
+  loop_fused_kernel<F, ND, NATIVE><<<grid, kFusedThreads, smem, stream>>>(args);
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
 }
@@ -535,7 +566,7 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   const int V3h = g.V3 / 2;
   args.c_begin = t_begin * V3h;
   args.c_end = t_end * V3h;
-  if (!choose_tiling(args.tl, grp, g, precision, fused_smem_limit_bytes(), args.c_begin, args.c_end))
+  if (!choose_tiling(args.tl, grp, g, precision, fused_smem_limit_bytes(), args.c_begin, args.c_end, vt.native))
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
   const int grid = (args.c_end - args.c_begin + args.tl.run - 1) / args.tl.run;
@@ -550,13 +581,98 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   const double flop_site = grp.nloops * (336.0 * 2 + 24.0) + (ul_off >= 0 ? 96.0 * 2 + (grp.nloops == 0 ? 24.0 : 0.0) : 0.0);
   ProfScope prof(K_LOOP_FUSED, stream, frac * (double)g.volume * (vt.nvec * S + grp.nloops * U + nl * Acc * (accumulate ? 2 : 1)),
                  frac * (double)g.volume * vt.nvec * flop_site);
-  switch (grp.nloops) {
-    case 0: return launch_fused_nd<F, 0>(args, smem, grid, stream);
-    case 1: return launch_fused_nd<F, 1>(args, smem, grid, stream);
-    case 2: return launch_fused_nd<F, 2>(args, smem, grid, stream);
-    case 3: return launch_fused_nd<F, 3>(args, smem, grid, stream);
-    default: return launch_fused_nd<F, 4>(args, smem, grid, stream);
+  if (vt.native) {  // eigenvectors in QUDA FLOAT2 order, staged as tensor boxes (vt.evec[] = their tensor maps)
+    switch (grp.nloops) {
+      case 0: return launch_fused_nd<F, 0, 1>(args, smem, grid, stream);
+      case 1: return launch_fused_nd<F, 1, 1>(args, smem, grid, stream);
+      case 2: return launch_fused_nd<F, 2, 1>(args, smem, grid, stream);
+      case 3: return launch_fused_nd<F, 3, 1>(args, smem, grid, stream);
+      default: return launch_fused_nd<F, 4, 1>(args, smem, grid, stream);
+    }
   }
+  switch (grp.nloops) {
+    case 0: return launch_fused_nd<F, 0, 0>(args, smem, grid, stream);
+    case 1: return launch_fused_nd<F, 1, 0>(args, smem, grid, stream);
+    case 2: return launch_fused_nd<F, 2, 0>(args, smem, grid, stream);
+    case 3: return launch_fused_nd<F, 3, 0>(args, smem, grid, stream);
+    default: return launch_fused_nd<F, 4, 0>(args, smem, grid, stream);
+  }
+}
+
+// ---- tensor maps of QUDA-ordered eigenvectors ------------------------------------------------------------------------------
+// A FLOAT2 field [parity][component][x_cb] is a 4-D tensor (16 reals = 8 sites, 12 components, volumeCB/8 chunks, 2 parities):
+// a box of (16, 12, NB, 1) lands in shared memory as NB x [component][8 sites], the layout the kernel's stage map expects.
+// Three maps per eigenvector (NB = 1, 2, 4), encoded on the host (cuTensorMapEncodeTiled, bound at run time: the library does
+// not link libcuda) and kept in device memory; the encoding depends on (address, lattice, precision) only, so it is cached.
+namespace {
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapCache {
+  std::mutex mu;
+  std::map<std::tuple<const void *, int, int>, int> slot;  // (field, volumeCB, precision) -> index
+  char *dev = nullptr;
+  int used = 0;
+  static constexpr int kCapacity = 16384;  // eigenvectors
+  static constexpr int kBytes = 3 * 128;   // three CUtensorMap objects
+};
+TmapCache &tmap_cache(int dev) {
+  static TmapCache c[64];
+  return c[(dev >= 0 && dev < 64) ? dev : 0];
+}
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmapEncodeFn>(p);
+  });
+  return fn;
+}
+}  // namespace
+
+int fused_native_tmaps(const void **tmap_d, const void *const *evec_d, int nvec, const LatGeom &g, int precision,
+                       cudaStream_t stream) {
+  if (g.volumeCB % kChunk)
+    return set_error(MUGIQ_B200_EINVAL, "loop plan: QUDA-ordered eigenvectors need volumeCB = %d to be a multiple of %d", g.volumeCB, kChunk);
+  TmapEncodeFn encode = tmap_encoder();
+  if (!encode) return set_error(MUGIQ_B200_ESTATE, "loop plan: cuTensorMapEncodeTiled is not available from this driver");
+  int dev = 0;
+  MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
+  TmapCache &c = tmap_cache(dev);
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (!c.dev) MUGIQ_CUDA_CHECK(cudaMalloc((void **)&c.dev, (size_t)TmapCache::kCapacity * TmapCache::kBytes));
+  const size_t pb = prec_bytes(precision);
+  for (int i = 0; i < nvec; i++) {
+    const auto key = std::make_tuple(evec_d[i], g.volumeCB, precision);
+    auto it = c.slot.find(key);
+    if (it == c.slot.end()) {
+      if (c.used == TmapCache::kCapacity) {  // start over: nothing in flight may still read the old entries
+        MUGIQ_CUDA_CHECK(cudaDeviceSynchronize());
+        c.slot.clear();
+        c.used = 0;
+      }
+      if ((uintptr_t)evec_d[i] & 15) return set_error(MUGIQ_B200_EINVAL, "loop plan: eigenvector %d is not 16-byte aligned", i);
+      alignas(64) CUtensorMap tm[3];
+      const cuuint64_t dim[4] = {16, 12, (cuuint64_t)g.volumeCB / kChunk, 2};
+      const cuuint64_t str[3] = {(cuuint64_t)g.volumeCB * 2 * pb, (cuuint64_t)kChunk * 2 * pb, (cuuint64_t)12 * g.volumeCB * 2 * pb};
+      const cuuint32_t es[4] = {1, 1, 1, 1};
+      for (int k = 0; k < 3; k++) {
+        const cuuint32_t box[4] = {16, 12, (cuuint32_t)(1 << k), 1};
+        const CUresult r = encode(&tm[k], pb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                  const_cast<void *>(evec_d[i]), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_error(MUGIQ_B200_ECUDA, "loop plan: cuTensorMapEncodeTiled failed with %d", (int)r);
+      }
+      static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+      MUGIQ_CUDA_CHECK(cudaMemcpyAsync(c.dev + (size_t)c.used * TmapCache::kBytes, tm, TmapCache::kBytes, cudaMemcpyHostToDevice, stream));
+      it = c.slot.emplace(key, c.used++).first;
+    }
+    tmap_d[i] = c.dev + (size_t)it->second * TmapCache::kBytes;
+  }
+  return MUGIQ_B200_OK;
 }
 
 int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,

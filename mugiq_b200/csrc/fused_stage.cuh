@@ -15,15 +15,18 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 // ---- stage map of a tile: the merged intervals of checkerboard-index space one eigenvector stage holds ------------
 // shared by host (sizing) and device (thread 0 of every CTA builds its own)
 constexpr int kMaxIv = kFusedMaxIv;
+constexpr int kChunk = 8;  // sites per chunk of a natively ordered (QUDA FLOAT2) stage
 struct StageMap {
-  int n;         // merged intervals = bulk copies per stage
+  int n;         // merged intervals
+  int ncp;       // bulk copies per stage (site-major: one per interval; FLOAT2: tensor boxes of 4, 2 or 1 chunks)
   int sites;     // sites per stage
-  int overflow;  // more than kMaxIv intervals (the host checks this before launching)
+  int overflow;  // more than kMaxIv intervals or copies (the host checks this before launching)
   int par[kMaxIv], lo[kMaxIv], hi[kMaxIv];  // interval [lo, hi) of checkerboard indices of parity par, sorted by (par, lo)
   int soff[kMaxIv];                          // first site of the interval inside the stage
   // the bulk copies, precomputed for the issuing lanes
   int cp_soff[kMaxIv];    // byte offset inside the stage
-  int cp_goff16[kMaxIv];  // offset inside the eigenvector, in units of 16 B
+  int cp_goff16[kMaxIv];  // site-major: offset inside the eigenvector in units of 16 B;
+                          // FLOAT2: first chunk | parity << 28 | box code << 29 (0, 1, 2: boxes of 1, 2, 4 chunks)
   int cp_bytes[kMaxIv];
 };
 
@@ -73,12 +76,27 @@ __host__ __device__ inline void iv_insert(StageMap &m, int lo, int hi) {
 // parities are staged for every image (a site's neighbour has parity p ^ (k & 1) and both own parities are in the tile),
 // so the interval list is built once and replicated.  Images of consecutive row pieces usually adjoin: they are joined
 // before they are inserted.
+//
+// align = 1: site-major eigenvectors, every interval is one linear bulk copy.  align = kChunk (QUDA FLOAT2 order,
+// [parity][spin*3+colour][x_cb]): intervals are widened to whole chunks of 8 sites, the stage holds them as
+// [chunk][component][8 sites] (1536 B per chunk in FP64) and they arrive as 4-D tensor boxes of 4, 2 or 1 chunks.
+__host__ __device__ inline void iv_insert_aligned(StageMap &m, int lo, int hi, int align, int limit) {
+  if (lo >= hi) return;
+  if (align > 1) {
+    lo = lo / align * align;
+    hi = (hi + align - 1) / align * align;
+    if (hi > limit) hi = limit;
+  }
+  iv_insert(m, lo, hi);
+}
+
 __host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &grp, const LatGeom &g, int site_bytes, int c0,
-                                                int c1) {
+                                                int c1, int align = 1) {
   m.n = 0;
   m.overflow = 0;
   const int Lh = g.Lh;
-  iv_insert(m, c0, c1);
+  const int vcb = g.volumeCB;
+  iv_insert_aligned(m, c0, c1, align, vcb);
   for (int j = 0; j < grp.nloops; j++) {
     const FusedLoop &lp = grp.loop[j];
     const int sh = lp.sign * lp.len;
@@ -98,11 +116,11 @@ __host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &g
           hi = Lh;
         }
         if (lo < 0) {
-          iv_insert(m, base + lo + Lh, base + Lh);
+          iv_insert_aligned(m, base + lo + Lh, base + Lh, align, vcb);
           lo = 0;
         }
         if (hi > Lh) {
-          iv_insert(m, base, base + hi - Lh);
+          iv_insert_aligned(m, base, base + hi - Lh, align, vcb);
           hi = Lh;
         }
         lo += base;
@@ -120,13 +138,13 @@ __host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &g
         if (lo < plo) plo = lo;
         if (hi > phi) phi = hi;
       } else {
-        iv_insert(m, plo, phi);
+        iv_insert_aligned(m, plo, phi, align, vcb);
         plo = lo;
         phi = hi;
       }
       c += b - a;
     }
-    iv_insert(m, plo, phi);
+    iv_insert_aligned(m, plo, phi, align, vcb);
   }
   // parity 0 block, then the same intervals for parity 1
   const int n = m.n;
@@ -138,13 +156,44 @@ __host__ __device__ inline void build_stage_map(StageMap &m, const FusedGroup &g
       m.lo[k] = m.lo[i];
       m.hi[k] = m.hi[i];
       m.soff[k] = off;
-      m.cp_soff[k] = off * site_bytes;
-      m.cp_goff16[k] = (int)((((long long)p * g.volumeCB + m.lo[i]) * site_bytes) >> 4);
-      m.cp_bytes[k] = (m.hi[i] - m.lo[i]) * site_bytes;
       off += m.hi[i] - m.lo[i];
     }
   m.n = 2 * n;
   m.sites = off;
+  if (align == 1) {
+    for (int k = 0; k < m.n; k++) {
+      m.cp_soff[k] = m.soff[k] * site_bytes;
+      m.cp_goff16[k] = (int)((((long long)m.par[k] * g.volumeCB + m.lo[k]) * site_bytes) >> 4);
+      m.cp_bytes[k] = (m.hi[k] - m.lo[k]) * site_bytes;
+    }
+    m.ncp = m.n;
+  } else {
+    int nc = 0;
+    for (int k = 0; k < m.n; k++) {
+      int chunk = m.lo[k] / kChunk, left = (m.hi[k] - m.lo[k]) / kChunk, pos = m.soff[k];
+      while (left > 0) {
+        const int code = left >= 4 ? 2 : (left >= 2 ? 1 : 0), nb = 1 << code;
+        if (nc == kMaxIv) {
+          m.overflow = 1;
+          break;
+        }
+        m.cp_soff[nc] = pos * site_bytes;  // a chunk holds kChunk sites of all 12 components: kChunk * site_bytes
+        m.cp_goff16[nc] = chunk | (m.par[k] << 28) | (code << 29);
+        m.cp_bytes[nc] = nb * kChunk * site_bytes;
+        nc++;
+        chunk += nb;
+        left -= nb;
+        pos += nb * kChunk;
+      }
+    }
+    m.ncp = nc;
+  }
+}
+
+// byte offset, inside a stage, of component 0 of the site at stage position pos
+template <int NATIVE> __host__ __device__ inline int stage_site_bytes(int pos, int site_bytes) {
+  // FLOAT2 stage: [chunk][component][8 sites]; a complex number is site_bytes / 12 bytes
+  return NATIVE ? (pos / kChunk) * (kChunk * site_bytes) + (pos % kChunk) * (site_bytes / 12) : pos * site_bytes;
 }
 
 // position (in sites) of checkerboard site cb of parity par inside the stage; -1 if the stage does not hold it
@@ -275,6 +324,14 @@ __device__ __forceinline__ void tma_bulk_g2s_if(uint32_t dst, const void *src_gm
       "{\n.reg .pred q;\nsetp.ne.b32 q, %4, 0;\n"
       "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}" ::"r"(dst),
       "l"(src_gmem), "r"(bytes), "r"(bar), "r"(pred)
+      : "memory");
+}
+// 4-D tensor box of a QUDA FLOAT2 eigenvector: coordinates (0, 0, chunk, parity) of the tensor (16 reals, 12 components,
+// volumeCB / 8 chunks, 2 parities); lands as [chunk][component][8 sites]
+__device__ __forceinline__ void tma_tensor4_g2s(uint32_t dst, const void *tmap, int chunk, int parity, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(tmap), "r"(0), "r"(0), "r"(chunk), "r"(parity), "r"(bar)
       : "memory");
 }
 }  // namespace mugiq_b200

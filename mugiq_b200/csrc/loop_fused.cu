@@ -183,16 +183,22 @@ static int plan_build(LoopPlan &pl, const void *gauge_d, cudaStream_t stream) {
 
 // Contribution of the given eigenvectors to every loop the plan computes, on the time-slices [t0, t1) only.
 int plan_accumulate_range(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
-                          int accumulate, int t0, int t1, bool zero_unreached, cudaStream_t stream) {
+                          int accumulate, int t0, int t1, bool zero_unreached, cudaStream_t stream, int evec_order) {
+  if (evec_order < 0) evec_order = pl.evec_order;
   char *pos = static_cast<char *>(dataPos_d);
   if (!accumulate && zero_unreached)
     for (int z : pl.zero_slots) MUGIQ_CUDA_CHECK(cudaMemsetAsync(pos + (size_t)z * pl.loop_bytes(), 0, pl.loop_bytes(), stream));
   for (int done = 0; done < nvec; done += kFusedMaxVec) {
     FusedVecTable vt;
     vt.nvec = std::min(kFusedMaxVec, nvec - done);
+    vt.native = evec_order == MUGIQ_B200_ORDER_SITE ? 0 : evec_order;
     for (int i = 0; i < vt.nvec; i++) {
       vt.evec[i] = evec_d[done + i];
       vt.inv_sigma[i] = inv_sigma_of(sigma_h[done + i], pl.precision);
+    }
+    if (vt.native) {  // QUDA FLOAT2 fields are staged through their tensor maps (encoded once per field, cached)
+      int rc = fused_native_tmaps(vt.evec, evec_d + done, vt.nvec, pl.g, pl.precision, stream);
+      if (rc) return rc;
     }
     for (size_t gi = 0; gi < pl.groups.size(); gi++) {
       // slot 0 (ultra-local) is accumulated by the first group
@@ -304,7 +310,7 @@ int mugiq_b200_loop_plan_create(mugiq_b200_loop_plan_t **plan, const void *gauge
 }
 
 int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int nentries, const mugiq_b200_geom_t *geom, int t_begin,
-                                  int t_end, int group, long long out[8]) {
+                                  int t_end, int group, int evec_order, long long out[8]) {
   const char *who = "mugiq_b200_fused_tiling_check";
   int rc = check_geom(geom, who);
   if (rc) return rc;
@@ -318,7 +324,7 @@ int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int ne
   if (group >= (int)pl.groups.size()) return set_error(MUGIQ_B200_EINVAL, "%s: the plan has %zu groups", who, pl.groups.size());
   if (t_end < 0) t_end = geom->L[3];
   if (t_begin < 0 || t_begin >= t_end || t_end > geom->L[3]) return set_error(MUGIQ_B200_EINVAL, "%s: bad time-slice range", who);
-  return fused_tiling_check(pl.groups[group], pl.g, pl.precision, t_begin, t_end, out);
+  return fused_tiling_check(pl.groups[group], pl.g, pl.precision, t_begin, t_end, evec_order == MUGIQ_B200_ORDER_FLOAT2, out);
 }
 
 int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan) {
@@ -348,6 +354,20 @@ int mugiq_b200_loop_plan_computed_slots(const mugiq_b200_loop_plan_t *plan, int 
   const int n = (int)plan->pl.comps.size();
   for (int i = 0; slots && i < n && i < max_slots; i++) slots[i] = plan->pl.comps[i].iL;
   return n;
+}
+
+int mugiq_b200_loop_plan_set_evec_order(mugiq_b200_loop_plan_t *plan, int order) {
+  const char *who = "mugiq_b200_loop_plan_set_evec_order";
+  if (!plan) return set_error(MUGIQ_B200_EINVAL, "%s: plan is NULL", who);
+  if (order == MUGIQ_B200_ORDER_FLOAT4)
+    return set_error(MUGIQ_B200_EINVAL, "%s: FLOAT4 fields are not staged directly (convert them with mugiq_b200_ingest_spinor_batch, "
+                     "or feed them through mugiq_b200_loop_feed_*)", who);
+  if (order != MUGIQ_B200_ORDER_SITE && order != MUGIQ_B200_ORDER_FLOAT2)
+    return set_error(MUGIQ_B200_EINVAL, "%s: unknown field order %d", who, order);
+  if (order == MUGIQ_B200_ORDER_FLOAT2 && plan->pl.g.volumeCB % 8)
+    return set_error(MUGIQ_B200_EINVAL, "%s: FLOAT2 staging needs volumeCB = %d to be a multiple of 8", who, plan->pl.g.volumeCB);
+  plan->pl.evec_order = order;
+  return MUGIQ_B200_OK;
 }
 
 int mugiq_b200_loop_plan_set_t_range(mugiq_b200_loop_plan_t *plan, int t_begin, int t_end) {

@@ -20,6 +20,7 @@ struct LoopPlan {
   int precision;
   int nLoop;
   bool symmetric;
+  int evec_order = MUGIQ_B200_ORDER_SITE;  // layout of the eigenvectors accumulate() is given (set_evec_order)
   int t_begin = 0, t_end = -1;  // time-slices the fused kernels compute (-1: all): interior of a lattice-T split slab
   std::vector<Comp> comps;
   std::vector<Derive> derives;
@@ -44,7 +45,8 @@ struct LoopPlan {
 const LoopPlan &plan_of(const mugiq_b200_loop_plan_t *plan);
 // Contribution of the given eigenvectors to every loop the plan computes, on the time-slices [t0, t1) only (t1 < 0: up
 // to Lt).  zero_unreached: also clear the slots no hop reaches (once per call, not once per chunk).
+// evec_order: layout of the fields (MUGIQ_B200_ORDER_SITE or _FLOAT2; < 0: the plan's own setting).
 int plan_accumulate_range(const LoopPlan &pl, void *dataPos_d, const void *const *evec_d, const double *sigma_h, int nvec,
-                          int accumulate, int t0, int t1, bool zero_unreached, cudaStream_t stream);
+                          int accumulate, int t0, int t1, bool zero_unreached, cudaStream_t stream, int evec_order = -1);
 
 }  // namespace mugiq_b200

@@ -247,7 +247,11 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
 
   const bool sharded = getLoopComm() && mugiqCommSize(getLoopComm()) > 1;
   const size_t fieldBytes = eigsolve->eVecs[0]->Bytes();
-  const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER;
+  // FLOAT2 fields (the order computeLoop dispatches MG-coarse and double-precision eigenvectors to,
+  // lib/interface_mugiq.cpp:226-235) are staged by the fused kernel itself; FLOAT4 fields are converted batch by batch
+  const bool direct2 = fieldOrder == QUDA_FLOAT2_FIELD_ORDER && cPrm->volumeCB % 8 == 0;
+  MUGIQ_CHECK(mugiq_b200_loop_plan_set_evec_order(plan, direct2 ? MUGIQ_B200_ORDER_FLOAT2 : MUGIQ_B200_ORDER_SITE));
+  const bool native = fieldOrder != QUDA_SPACE_SPIN_COLOR_FIELD_ORDER && !direct2;
   if (eigsolve->producer) {
     // Streamed eigenvectors (the reference's prolongateEvec / field copy per eigenvector, lib/loop_mugiq.cpp:478-483,
     // batched): the library's feed hands out device staging batches, the producer fills batch b+1 on its stream while
@@ -255,7 +259,9 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
     const int batch = std::max(1, std::min({eigsolve->producerBatch, nEv, 256}));
     if (!feed || feedBatch != batch) {
       if (feed) mugiq_b200_loop_feed_destroy(feed);
-      MUGIQ_CHECK(mugiq_b200_loop_feed_create(&feed, plan, dataPos_d, batch, 2, native ? abi_order(fieldOrder) : MUGIQ_B200_ORDER_SITE, 0, nullptr));
+      MUGIQ_CHECK(mugiq_b200_loop_feed_create(&feed, plan, dataPos_d, batch, 2,
+                                              fieldOrder == QUDA_SPACE_SPIN_COLOR_FIELD_ORDER ? MUGIQ_B200_ORDER_SITE : abi_order(fieldOrder), 0,
+                                              nullptr));
       feedBatch = batch;
     } else {
       MUGIQ_CHECK(mugiq_b200_loop_feed_set_plan(feed, plan, dataPos_d));

@@ -29,9 +29,15 @@ class Eigsolve:
     or HOST tensors when the loop streams them) and `eVals_sigma[n]` (host floats, sigma_n = sqrt(lambda_n),
     lib/eigsolve_mugiq.cpp:289-315).  `L` are the local lattice extents the fields live on."""
 
-    def __init__(self, eVecs, eVals_sigma, L, ext_volume=0):
+    def __init__(self, eVecs, eVals_sigma, L, ext_volume=0, field_order=0):
         # ext_volume: sites of the T-split extended slab when the fields are stored with their halo slices allocated
         self.ext_volume = int(ext_volume)
+        # field_order: 0 = canonical site-major, 2 = QUDA FLOAT2 ([parity][spin*3+colour][x_cb]; what
+        # computeLoop dispatches on, lib/interface_mugiq.cpp:226-235): staged by the fused kernel itself, no conversion
+        self.field_order = int(field_order)
+        if self.field_order not in (0, 2):
+            raise MugiqError("Eigsolve: field_order must be 0 (site-major) or 2 (QUDA FLOAT2); convert FLOAT4 fields with "
+                             "ops.ingest_spinor_batch")
         self.eVecs = list(eVecs)
         self.eVals_sigma = [float(s) for s in eVals_sigma]
         self.L = tuple(int(x) for x in L)
@@ -384,6 +390,10 @@ class Loop_Mugiq:
             entries = p.entries() if p.doNonLocal else []
             gauge = self.displace.gaugeField if self.displace is not None else None
             self._plan = ops.LoopPlan(gauge, entries, self.L_run, self.precision)
+            if self.eigsolve.field_order:
+                if self.tsplit is not None:
+                    raise MugiqError("Loop_Mugiq: the lattice-T split takes site-major eigenvectors")
+                self._plan.set_evec_order(self.eigsolve.field_order)
             self._plan_version = version
         return self._plan
 
@@ -397,7 +407,7 @@ class Loop_Mugiq:
         if getattr(self, "_feed", None) is None or self._feed.batch != nb:
             if getattr(self, "_feed", None) is not None:
                 self._feed.close()
-            self._feed = ops.LoopFeed(plan, self.dataPos_d, batch=nb, nbuf=2)
+            self._feed = ops.LoopFeed(plan, self.dataPos_d, batch=nb, nbuf=2, order=es.field_order)
         elif self._feed.plan is not plan or self._feed.dataPos is not self.dataPos_d:
             self._feed.set_plan(plan, self.dataPos_d)   # the plan was rebuilt for a new gauge field
         self._feed.push_host(es.eVecs, es.eVals_sigma)

@@ -233,6 +233,10 @@ class LoopPlan:
         check(_lib.load().mugiq_b200_loop_plan_computed_slots(self._h, arr, n))
         return list(arr)
 
+    def set_evec_order(self, order):
+        """0: canonical site-major eigenvectors (default); 2: QUDA FLOAT2 fields, staged by the fused kernel itself."""
+        check(_lib.load().mugiq_b200_loop_plan_set_evec_order(self._h, int(order)))
+
     def set_t_range(self, t_begin, t_end):
         """accumulate() computes only the time-slices [t_begin, t_end) (interior of a lattice-T split slab)."""
         check(_lib.load().mugiq_b200_loop_plan_set_t_range(self._h, int(t_begin), int(t_end)))

@@ -191,3 +191,52 @@ def test_resident_batches_follow_changed_sigma_and_refilled_buffers(oracle):
     mixed = np.concatenate([ev[nEv:nEv + 2], ev[0:1], ev[nEv + 3:]])
     loop.computeCoarseLoop()
     assert rel_err(loop.dataPos_d.cpu().numpy(), oracle.compute_loop(mixed, sig2, U, entries, L)) < TOL_F64
+
+
+@pytest.mark.parametrize("L,entries_text,p2", [((16, 16, 16, 32), synth.ONE_HOP_ENTRIES, 1), ((24, 24, 24, 48), synth.UP_TO_4_ENTRIES, 0),
+                                              ((8, 4, 4, 8), "+x:1,3;-y:2;+t:1;-t:1;+z:2", 1), ((4, 4, 4, 8), "", 1)])
+def test_quda_float2_eigenvectors_are_staged_directly(oracle, L, entries_text, p2):
+    """Eigenvectors handed over in QUDA's native FLOAT2 order ([parity][spin*3+colour][x_cb], what FieldOrderCB gives the
+    reference's kernels, lib/mugiq_contract_kernels.cu:82-83): the fused kernel fetches them as TMA tensor boxes, no
+    conversion pass.  Same oracle, same tolerance; device-resident and host-streamed (feed) eigenvectors."""
+    from mugiq_b200.loop import Loop_Mugiq, Eigsolve
+    from oracle import ref_kernels as rk
+    from oracle import numpy_check as npc
+    nEv = 5 if L[0] <= 8 else 3
+    ev = synth.random_evecs_np(L, nEv, seed=206)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=206) if entries_text else None
+    mom = momenta_up_to(p2)
+    prm = MugiqLoopParam(gauge=[U[mu] for mu in range(4)] if U is not None else None)
+    if entries_text:
+        prm.set_displacements(entries_text)
+    prm.set_momenta(mom)
+    evq = [rk.site_to_quda(torch.from_numpy(ev[n]).cuda(), 2) for n in range(nEv)]
+    loop = Loop_Mugiq(prm, Eigsolve(evq, sig, L, field_order=2), evec_batch=2, copy_pos_to_host=False)
+    loop.computeCoarseLoop()
+    ref = oracle.compute_loop(ev, sig, U, entry_list(entries_text), L)
+    ref_d = torch.from_numpy(ref).cuda()
+    assert rel_err_t(loop.dataPos_d, ref_d) < TOL_F64
+    if L[0] <= 16:
+        assert rel_err(loop.dataMom.numpy(), npc.momentum_projection_mm(ref, mom, -1, L)) < TOL_F64
+    # the same fields from pinned host memory through the streamed feed (FLOAT2 staging batches, no conversion)
+    evq_h = [v.cpu().pin_memory() for v in evq]
+    loop_h = Loop_Mugiq(prm, Eigsolve(evq_h, sig, L, field_order=2), stream_batch=2, copy_pos_to_host=False)
+    loop_h.computeCoarseLoop()
+    assert rel_err_t(loop_h.dataPos_d, ref_d) < TOL_F64
+
+
+def test_quda_float2_single_precision(oracle):
+    from mugiq_b200.loop import Loop_Mugiq, Eigsolve
+    from oracle import ref_kernels as rk
+    L, nEv = (8, 4, 4, 8), 4
+    ev = synth.random_evecs_np(L, nEv, seed=207)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=207)
+    prm = MugiqLoopParam(gauge=[U[mu].astype(np.complex64) for mu in range(4)])
+    prm.set_displacements("+x:1;-z:1,2;+t:2")
+    evq = [rk.site_to_quda(torch.from_numpy(ev[n].astype(np.complex64)).cuda(), 2) for n in range(nEv)]
+    loop = Loop_Mugiq(prm, Eigsolve(evq, sig, L, field_order=2), copy_pos_to_host=False)
+    loop.computeCoarseLoop()
+    ref = oracle.compute_loop(ev, sig, U, entry_list("+x:1;-z:1,2;+t:2"), L)
+    assert rel_err(loop.dataPos_d.cpu().numpy(), ref) < 2e-5

@@ -69,17 +69,17 @@ def test_group_size_does_not_depend_on_the_row_length():
     assert wide["computed"] == narrow["computed"] == 5
 
 
-def tiling(L, entries, t_begin=0, t_end=-1, precision=8):
+def tiling(L, entries, t_begin=0, t_end=-1, precision=8, order=0):
     """mugiq_b200_fused_tiling_check for every launch group: [{run, units, nstages, stage_bytes, max_copies, mean_sites,
     misses, bad_maps}]."""
     lib = _lib.load()
     g = _lib.make_geom(L, precision)
     out = (C.c_longlong * 8)()
-    ngroups = lib.mugiq_b200_fused_tiling_check(_lib.entry_array(entries), len(entries), C.byref(g), t_begin, t_end, -1, out)
+    ngroups = lib.mugiq_b200_fused_tiling_check(_lib.entry_array(entries), len(entries), C.byref(g), t_begin, t_end, -1, order, out)
     assert ngroups >= 1, lib.mugiq_b200_last_error()
     res = []
     for gi in range(ngroups):
-        assert lib.mugiq_b200_fused_tiling_check(_lib.entry_array(entries), len(entries), C.byref(g), t_begin, t_end, gi,
+        assert lib.mugiq_b200_fused_tiling_check(_lib.entry_array(entries), len(entries), C.byref(g), t_begin, t_end, gi, order,
                                                  out) == 0, lib.mugiq_b200_last_error()
         res.append(dict(zip(("run", "units", "nstages", "stage_bytes", "max_copies", "mean_sites", "misses", "bad_maps"), out)))
     return res
@@ -106,6 +106,35 @@ def test_every_thread_finds_its_sites_in_the_stage(L, entries, t_range):
         for t in tiling(L, entries, *t_range, precision=prec):
             assert t["misses"] == 0 and t["bad_maps"] == 0, t
             assert t["run"] == 16 * t["units"] and t["nstages"] >= 2 and t["max_copies"] <= 64, t
+
+
+@pytest.mark.parametrize("L,entries,t_range", [
+    ((4, 4, 4, 8), ONEHOP8 + [(2, 1, 2, 3)], (0, -1)),
+    ((16, 16, 16, 32), ONEHOP8, (0, -1)),
+    ((24, 24, 24, 48), UP_TO_4, (0, -1)),
+    ((32, 32, 32, 64), [], (0, -1)),
+    ((48, 48, 48, 16), ONEHOP8, (2, 14)),
+    ((12, 2, 2, 2), [(0, 1, 1, 7), (0, 0, 2, 9)], (0, -1)),
+])
+def test_float2_stages_are_whole_chunks_fetched_as_tensor_boxes(L, entries, t_range):
+    """Eigenvectors in QUDA FLOAT2 order: every interval of a stage is widened to chunks of 8 sites and fetched as tensor
+    boxes of 4, 2 or 1 chunks; the boxes must tile the stage exactly and every thread's sites must still be in it."""
+    for prec in (8, 4):
+        for t in tiling(L, entries, *t_range, precision=prec, order=2):
+            assert t["misses"] == 0 and t["bad_maps"] == 0, t
+            assert t["nstages"] >= 2 and t["max_copies"] <= 64, t
+
+
+def test_float2_staging_needs_whole_chunks_per_parity():
+    lib = _lib.load()
+    g = _lib.make_geom((6, 6, 6, 6), 8)   # volumeCB = 648 = 81 * 8: fine
+    out = (C.c_longlong * 8)()
+    assert lib.mugiq_b200_fused_tiling_check(_lib.entry_array(ONEHOP8), 8, C.byref(g), 0, -1, 0, 2, out) == 0
+    # with even extents volumeCB is always a multiple of 8; odd extents (ultra-local loop only) can break it
+    g = _lib.make_geom((2, 3, 3, 3), 8)   # volumeCB = 27
+    assert lib.mugiq_b200_fused_tiling_check(_lib.entry_array([]), 0, C.byref(g), 0, -1, 0, 2, out) == -1
+    assert b"multiple of 8" in lib.mugiq_b200_last_error()
+    assert lib.mugiq_b200_fused_tiling_check(_lib.entry_array([]), 0, C.byref(g), 0, -1, 0, 0, out) == 0
 
 
 def test_runs_fill_every_lane_on_the_baseline_lattices():
