@@ -635,9 +635,12 @@ def leg_tsplit(h, steps, warmup):
            "loop_fused_ms_per_step": rep.get("loop_fused", {}).get("ms", 0.0) / steps}
     hp = rep.get("halo_push")
     if hp and hp["ms"] > 0:
-        out["halo_bytes_per_step"] = hp["alg_bytes"] / steps
+        # the library counts a push as read + write; what crosses NVLink is half of that, one way (upper halos only:
+        # the minus-t loop is derived from its plus partner)
+        out["halo_bytes_sent_per_step"] = hp["alg_bytes"] / 2 / steps
         out["halo_push_ms_per_step"] = hp["ms"] / steps
-        out["halo_GBps_per_direction"] = hp["alg_bytes"] / (hp["ms"] * 1e-3) / 1e9
+        out["halo_GBps_per_direction"] = hp["alg_bytes"] / 2 / (hp["ms"] * 1e-3) / 1e9
+        out["halo_frac_of_770"] = out["halo_GBps_per_direction"] / 770.0
     del loop
     cleanup()
     del es, U

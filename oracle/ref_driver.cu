@@ -182,4 +182,103 @@ int mugiq_ref_loop(void *dataPos_d, void *const *evec_d, const double *sigma, in
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// The same loop nest with CUDA events around the reference's KERNELS only: the argument structs are staged before the
+// timed region and nothing is allocated, freed or synchronised inside it, i.e. what the reference's kernels cost on this
+// GPU without the per-call cudaMalloc / cudaMemcpy / cudaDeviceSynchronize / cudaFree of its wrappers
+// (lib/contract_wrappers.cu:93-114,176-196).  Launch geometry restated from the wrappers (:103-110, :186-191).
+// out_ms[0] = contraction kernels, [1] = displacement kernels, [2] = the field copies / zeroing of the loop nest
+// (lib/loop_mugiq.cpp:482-487, lib/displace.cpp:47-67); out_n[0..2] = how many of each.  FLOAT2 order, FP64.
+int mugiq_ref_loop_kernel_times(void *dataPos_d, void *const *evec_d, const double *sigma, int nev, void *gauge_d,
+                                const int *entries, int nentries, const int L[4], void *work_d, float out_ms[3], int out_n[3]) {
+  typedef LoopContractArg<double, QUDA_FLOAT2_FIELD_ORDER> CArg;
+  typedef CovDispVecArg<double, QUDA_FLOAT2_FIELD_ORDER> DArg;
+  gamma_tables(8);
+  Quiet q(true);
+  const size_t V4 = (size_t)L[0] * L[1] * L[2] * L[3];
+  const size_t fbytes = V4 * 12 * sizeof(complex<double>);
+  const size_t perLoop = 16 * V4;
+  char *w = static_cast<char *>(work_d);
+  void *fineL = w, *fineR = w + fbytes, *aux = w + 2 * fbytes;
+  complex<double> *pos = static_cast<complex<double> *>(dataPos_d);
+  CArg *carg_d;
+  DArg *darg_d;
+  cudaMalloc((void **)&carg_d, sizeof(CArg));
+  cudaMalloc((void **)&darg_d, sizeof(DArg));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int k = 0; k < 3; k++) {
+    out_ms[k] = 0;
+    out_n[k] = 0;
+  }
+  auto timed = [&](int k, auto &&fn) {
+    cudaEventRecord(e0);
+    fn();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    out_ms[k] += ms;
+    out_n[k]++;
+  };
+  ColorSpinorField fL(fineL, L, QUDA_FLOAT2_FIELD_ORDER, QUDA_DOUBLE_PRECISION), fR(fineR, L, QUDA_FLOAT2_FIELD_ORDER, QUDA_DOUBLE_PRECISION),
+      fA(aux, L, QUDA_FLOAT2_FIELD_ORDER, QUDA_DOUBLE_PRECISION);
+  cudaGaugeField gf(gauge_d, L, QUDA_GHOST_EXCHANGE_EXTENDED);
+  auto contract = [&](complex<double> *loop_d, double sg) {
+    CArg arg(fL, fR, sg);
+    cudaMemcpy(carg_d, &arg, sizeof(arg), cudaMemcpyHostToDevice);
+    dim3 blockDim(THREADS_PER_BLOCK, arg.nParity, SHMEM_BLOCK_Z_SIZE);
+    dim3 gridDim((arg.volumeCB + blockDim.x - 1) / blockDim.x, 1, 1);
+    const size_t shmem = sizeof(complex<double>) * NELEM_SHMEM_CPLX_BUF * blockDim.x * blockDim.y;
+    timed(0, [&] { loopContract_kernel<double, CArg><<<gridDim, blockDim, shmem>>>(loop_d, carg_d); });
+  };
+  size_t loopOffset = 1;
+  for (int id = -1; id < nentries; id++) {
+    const int dir = id < 0 ? 0 : entries[4 * id], sign = id < 0 ? 0 : entries[4 * id + 1];
+    const int start = id < 0 ? 0 : entries[4 * id + 2], stop = id < 0 ? 0 : entries[4 * id + 3];
+    const size_t nL = id < 0 ? 1 : (size_t)(stop - start + 1);
+    const size_t bufOffset = id < 0 ? 0 : perLoop * loopOffset;
+    cudaMemset(pos + bufOffset, 0, sizeof(complex<double>) * perLoop * nL);
+    for (int n = 0; n < nev; n++) {
+      timed(2, [&] {
+        cudaMemcpyAsync(fineL, evec_d[n], fbytes, cudaMemcpyDeviceToDevice);
+        cudaMemcpyAsync(fineR, fineL, fbytes, cudaMemcpyDeviceToDevice);
+      });
+      if (id >= 0) {
+        int dispCount = 0;
+        for (int idisp = 1; idisp <= stop; idisp++) {
+          timed(2, [&] { cudaMemsetAsync(aux, 0, fbytes); });
+          {
+            DArg arg(fA, fR, gf);
+            cudaMemcpy(darg_d, &arg, sizeof(arg), cudaMemcpyHostToDevice);
+            dim3 blockDim(THREADS_PER_BLOCK, arg.nParity, 1);
+            dim3 gridDim((arg.volumeCB + blockDim.x - 1) / blockDim.x, 1, 1);
+            timed(1, [&] {
+              covariantDisplacementVector_kernel<double, DArg, QUDA_FLOAT2_FIELD_ORDER><<<gridDim, blockDim>>>(darg_d, (DisplaceDir)dir,
+                                                                                                             (DisplaceSign)sign);
+            });
+          }
+          timed(2, [&] {
+            cudaMemcpyAsync(fineR, aux, fbytes, cudaMemcpyDeviceToDevice);
+            cudaMemcpyAsync(aux, fineR, fbytes, cudaMemcpyDeviceToDevice);
+          });
+          if (idisp >= start && idisp <= stop) {
+            contract(pos + bufOffset + perLoop * dispCount, sigma[n]);
+            dispCount++;
+          }
+        }
+      } else {
+        contract(pos, sigma[n]);
+      }
+    }
+    if (id >= 0) loopOffset += nL;
+  }
+  cudaDeviceSynchronize();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(carg_d);
+  cudaFree(darg_d);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 }  // extern "C"

@@ -121,3 +121,27 @@ def compute_loop(evecs_q, sigma, gauge, entries, L, order=2):
     _ok(lib().mugiq_ref_loop(_p(pos), ptrs, sig, n, _p(gauge) if gauge is not None else None, ent, len(entries), _i4(L),
                              int(order), _p(work)), "mugiq_ref_loop")
     return pos
+
+
+def kernel_only_ms(evecs_q, sigma, gauge, entries, L):
+    """The reference's loop nest with CUDA events around its KERNELS only (argument structs pre-staged, no allocation or
+    synchronisation in the timed regions): {"ms": contraction + displacement kernels, "contract_ms", "displace_ms",
+    "field_copies_ms", "launches", "note"}.  FLOAT2 order, FP64."""
+    V4 = int(L[0]) * int(L[1]) * int(L[2]) * int(L[3])
+    nLoop = 1 + sum(b - a + 1 for (_, _, a, b) in entries)
+    pos = torch.zeros((nLoop, 16, V4), dtype=torch.complex128, device="cuda")
+    work = torch.empty((3, V4, 12), dtype=torch.complex128, device="cuda")
+    n = len(evecs_q)
+    ptrs = (C.c_void_p * n)(*[v.data_ptr() for v in evecs_q])
+    sig = (C.c_double * n)(*[float(s) for s in sigma])
+    ent = (C.c_int * max(4 * len(entries), 1))(*[int(x) for e in entries for x in e])
+    ms = (C.c_float * 3)()
+    cnt = (C.c_int * 3)()
+    torch.cuda.synchronize()
+    _ok(lib().mugiq_ref_loop_kernel_times(_p(pos), ptrs, sig, n, _p(gauge) if gauge is not None else None, ent, len(entries), _i4(L),
+                                          _p(work), ms, cnt), "mugiq_ref_loop_kernel_times")
+    return {"ms": ms[0] + ms[1], "contract_ms": ms[0], "displace_ms": ms[1], "field_copies_ms": ms[2],
+            "launches": cnt[0] + cnt[1],
+            "note": "CUDA events around loopContract_kernel / covariantDisplacementVector_kernel only (launch geometry of "
+                    "lib/contract_wrappers.cu:103-110,186-191, argument structs staged outside the timed regions); the field "
+                    "copies and zeroing of the loop nest are timed separately"}

@@ -172,3 +172,17 @@ def test_reference_loop_nest(ref, ops, oracle, L, entries):
     ph = ref.phase_matrix(mom, -1, L)                              # [Nmom, V3]
     dm = torch.matmul(ph, mp.reshape(V3, 16 * nLoop * Lt))         # dataMom[im][idata][t]
     assert rel_err(loop.dataMom.numpy().reshape(len(mom), -1), host(dm)) < TOL_F64
+
+
+def test_reference_kernel_only_timing(ref, ops):
+    """bench.py's `reference_gpu.kernel_only`: the reference's loop nest with CUDA events around its kernels only (argument
+    structs pre-staged).  Checks the bookkeeping: one contraction per (eigenvector, loop), `stop` hops per eigenvector and
+    entry, positive times."""
+    L, nEv = (4, 4, 4, 8), 3
+    ev = synth.random_evecs_np(L, nEv, seed=54)
+    U = synth.random_gauge(L, seed=54)
+    entries = [(0, 1, 1, 1), (3, 0, 2, 3)]
+    gd = ops.gauge_upload(U, L)
+    k = ref.kernel_only_ms([ref.site_to_quda(dev(ev[i]), 2) for i in range(nEv)], synth.sigmas(nEv), gd, entries, L)
+    assert k["launches"] == nEv * (1 + 1 + 2) + nEv * (1 + 3)   # contractions + hops
+    assert k["contract_ms"] > 0 and k["displace_ms"] > 0 and k["field_copies_ms"] > 0 and abs(k["ms"] - k["contract_ms"] - k["displace_ms"]) < 1e-6
