@@ -26,6 +26,26 @@ def write_momentum_loops(filename, loop):
         np.savez(filename, **data)
 
 
+def write_momentum_loops_time_ranks(filename, loop, rank, world, barrier):
+    """The reference's parallel write (lib/loop_mugiq.cpp:530-656) for a lattice split in t over `world` time ranks: rank 0
+    lays out the HDF5 file with every [totT][2] dataset (zero-filled), `barrier()` makes it visible, then EVERY rank writes
+    its own rows [rank*locT, +locT) of every dataset from its local dataMom - the hyperslab of :561-565, :624 - and a
+    second barrier closes the collective.  Serial and parallel files are byte-identical."""
+    from . import h5min
+    local = {"/" + k: v for k, v in momentum_loop_datasets(loop).items()}   # [locT][2] each
+    dt = next(iter(local.values())).dtype
+    locT = next(iter(local.values())).shape[0]
+    shapes = {k: (locT * world, 2) for k in local}
+    if rank == 0:
+        offs = h5min.skeleton(filename, shapes, dtype=dt)
+    else:
+        offs = h5min.offsets(shapes, dtype=dt)
+    barrier()
+    for k, v in local.items():
+        h5min.write_rows(filename, offs[k], rank * locT, v)
+    barrier()
+
+
 def read_loops_file(path):
     """Reads the flat loop file the C++ host mirror writes (Loop_Mugiq::writeLoopsHDF5_Mom in
     mugiq_b200/host/src/loop_mugiq.cpp): text index + raw values.  Returns {hdf5 path: complex array [T]}."""

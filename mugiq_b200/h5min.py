@@ -91,6 +91,7 @@ class _Writer:
     def __init__(self, leaf_k):
         self.leaf_k = leaf_k
         self.buf = bytearray(96)  # superblock written last
+        self.raw_offset = {}      # dataset path -> byte offset of its raw data in the file
 
     def alloc(self, data):
         off = len(self.buf)
@@ -98,8 +99,10 @@ class _Writer:
         self.buf += _pad8(bytes(data))
         return off
 
-    def dataset(self, arr):
+    def dataset(self, arr, path=None):
         raw = self.alloc(arr.tobytes()) if arr.size else UNDEF
+        if path is not None:
+            self.raw_offset[path] = raw
         space = struct.pack("<BBB5x", 1, arr.ndim, 0) + b"".join(struct.pack("<Q", d) for d in arr.shape)
         fill = struct.pack("<BBBB", 2, 2, 2, 0)  # v2: allocate late, write fill if set, fill value undefined
         layout = struct.pack("<BBQQ", 3, 1, raw, arr.nbytes)
@@ -107,7 +110,7 @@ class _Writer:
         return self.alloc(_object_header([_message(0x0001, space, 0), _message(0x0003, _datatype_float(arr.itemsize), 1),
                                           _message(0x0005, fill, 1), _message(0x0008, layout, 1)]))
 
-    def group(self, node):
+    def group(self, node, prefix=""):
         """Writes the objects below `node`, then its heap, symbol-table node, B-tree and object header.
         Returns (object header address, B-tree address, heap address)."""
         names = sorted(node.children, key=lambda s: s.encode())
@@ -115,10 +118,10 @@ class _Writer:
         for name in names:
             child = node.children[name]
             if isinstance(child, _Node):
-                oh, bt, hp = self.group(child)
+                oh, bt, hp = self.group(child, prefix + "/" + name)
                 entries.append((name, oh, 1, struct.pack("<QQ", bt, hp)))
             else:
-                entries.append((name, self.dataset(child), 0, b"\0" * 16))
+                entries.append((name, self.dataset(child, prefix + "/" + name), 0, b"\0" * 16))
         # local heap: "" at offset 0, then the names; a 16-byte free block closes the segment
         heap = bytearray(_pad8(b"\0"))
         offs = []
@@ -170,6 +173,50 @@ def write(filename, datasets):
     with open(filename, "wb") as fh:
         fh.write(blob)
     return len(blob)
+
+
+# ---- several writers, one file: what the reference does with MPI-IO and hyperslabs ---------------------------------------
+# writeLoopsHDF5_Mom opens the file collectively (H5Pset_fapl_mpio, /root/reference/lib/loop_mugiq.cpp:571-572), creates every
+# [totT][2] dataset on all ranks and lets each "time process" write its rows [tCoord*locT, +locT) (:561-565, :624).  With
+# contiguous datasets that is: ONE rank lays the file out (metadata + zero-filled raw data), then every rank writes its rows
+# at (raw data offset of the dataset) + row0 * (bytes per row) - positional writes into disjoint byte ranges of a shared file.
+def skeleton(filename, shapes, dtype=np.float64):
+    """Writes the file with every dataset of `shapes` ({path: shape}) zero-filled and returns {path: raw data offset}.
+    The layout depends on the paths and shapes only: every rank can compute the same offsets with `offsets()`."""
+    w, root = _layout(shapes, dtype)
+    blob = w.finish(root)
+    with open(filename, "wb") as fh:
+        fh.write(blob)
+    return dict(w.raw_offset)
+
+
+def _layout(shapes, dtype):
+    datasets = {p: np.zeros(shape, dtype=dtype) for p, shape in shapes.items()}
+    root = _tree(datasets)
+    leaf_k = max(4, (_max_entries(root) + 1) // 2)
+    if leaf_k > 0xFFFF:
+        raise ValueError("too many links in one group")
+    return _Writer(leaf_k), root
+
+
+def offsets(shapes, dtype=np.float64):
+    """{path: raw data offset} of the file `skeleton` writes for these shapes, without writing anything."""
+    w, root = _layout(shapes, dtype)
+    w.finish(root)
+    return dict(w.raw_offset)
+
+
+def write_rows(filename, offset, row0, rows):
+    """Rows [row0, row0 + len(rows)) of the dataset whose raw data start at byte `offset` of an existing file
+    (the hyperslab [tCoord*locT, +locT) of lib/loop_mugiq.cpp:624).  `rows`: C-contiguous array, first axis = rows."""
+    import os
+    rows = np.ascontiguousarray(rows)
+    row_bytes = rows.nbytes // max(rows.shape[0], 1)
+    fd = os.open(filename, os.O_WRONLY)
+    try:
+        os.pwrite(fd, rows.tobytes(), offset + row0 * row_bytes)
+    finally:
+        os.close(fd)
 
 
 # ---- reader (old-style groups, v1 object headers, contiguous / compact float and integer datasets) ---------------------

@@ -468,8 +468,14 @@ class Loop_Mugiq:
                 warnings.warn("writeLoopsHDF5: Performed momentum projection, but got writeDatMom = FALSE. "
                               "Will proceed to write momentum-space loop data")
                 self.writeDataMom = True
-            from .h5lite import write_momentum_loops
-            write_momentum_loops(self.momSpaceFilename, self)
+            from .h5lite import write_momentum_loops, write_momentum_loops_time_ranks
+            ts = self.tsplit
+            if ts is not None and ts.world > 1 and str(self.momSpaceFilename).lower().endswith((".h5", ".hdf5")):
+                # every time rank writes its own rows of every [totT][2] dataset (lib/loop_mugiq.cpp:561-572,624)
+                import torch.distributed as dist
+                write_momentum_loops_time_ranks(self.momSpaceFilename, self, ts.rank, ts.world, lambda: dist.barrier(group=self.group))
+            elif ts is None or ts.rank == 0:
+                write_momentum_loops(self.momSpaceFilename, self)
         elif not self.writeDataPos:
             warnings.warn("writeLoopsHDF5: Did not perform momentum projection, but got writeDatPos = FALSE. "
                           "Will proceed to write position-space loop data")

@@ -134,3 +134,36 @@ int main(int, char **argv) {
     assert len(h) == 10 and h["/single/loop"].dtype == np.float32 and h["/mom_+1_+0_-1/disp_+z_10/g1g2/loop"].shape == (12, 2)
     assert np.array_equal(h["/mom_-1_+0_+1/disp_+z_1/1/loop"].ravel(), 0.25 * np.arange(24) - 1.0)
     assert h5min.dumps(h) == blob
+
+
+def test_time_ranks_write_their_rows_into_one_file(tmp_path):
+    """The reference's parallel write (MPI-IO + hyperslabs, lib/loop_mugiq.cpp:561-572,624): rank 0 lays the file out, every
+    time rank writes its rows [rank*locT, +locT) of every [totT][2] dataset.  The result must be byte-identical to the
+    serial file, whatever the order the ranks write in."""
+    from mugiq_b200 import h5min
+    rng = np.random.default_rng(3)
+    T, world = 12, 3
+    names = ["/mom_%+d_+0_+0/disp_%s/%s/loop" % (p, d, g) for p in (-1, 0, 1) for d in ("0", "+z_1", "-t_10") for g in ("G0", "G5", "G15")]
+    full = {n: rng.standard_normal((T, 2)) for n in names}
+    serial = tmp_path / "serial.h5"
+    h5min.write(serial, full)
+    par = tmp_path / "parallel.h5"
+    shapes = {n: (T, 2) for n in names}
+    offs = h5min.skeleton(par, shapes)
+    assert offs == h5min.offsets(shapes)                      # every rank can derive the layout itself
+    assert all(np.array_equal(v, np.zeros((T, 2))) for v in h5min.read(par).values())
+    locT = T // world
+    for rank in (2, 0, 1):
+        for n in names:
+            h5min.write_rows(par, offs[n], rank * locT, full[n][rank * locT:(rank + 1) * locT])
+    assert par.read_bytes() == serial.read_bytes()
+    got = h5min.read(par)
+    assert set(got) == set(names) and all(np.array_equal(got[n], full[n]) for n in names)
+    # single precision
+    f32 = {n: v.astype(np.float32) for n, v in full.items()}
+    h5min.write(serial, f32)
+    offs = h5min.skeleton(par, shapes, dtype=np.float32)
+    for rank in range(world):
+        for n in names:
+            h5min.write_rows(par, offs[n], rank * locT, f32[n][rank * locT:(rank + 1) * locT])
+    assert par.read_bytes() == serial.read_bytes()

@@ -121,6 +121,24 @@ def _worker(rank, world, port, out_dir):
     ok = ok and torch.equal(pv[[1, 3]][:, :, :, ts.H - 1:ts.H], want_ext[[1, 3]][:, :, :, ts.H - 1:ts.H]) and bool((pv[[1, 3]][:, :, :, :ts.H - 1] == 0).all())
     ts.exchange_loop_halo(pos_ext, [1, 3], group=dist.group.WORLD)
     ok = ok and torch.equal(pv[[1, 3]][:, :, :, :ts.H], want_ext[[1, 3]][:, :, :, :ts.H]) and bool((pv[[0, 2]][:, :, :, :ts.H] == 0).all())
+    # the loop file written by all time ranks at once (lib/loop_mugiq.cpp:561-572,624): rank 0 lays it out, everybody
+    # writes its own rows; compared with the serial file of the gathered data
+    from mugiq_b200 import h5lite, h5min
+
+    class FakeLoop:  # what h5lite reads from a Loop_Mugiq: {(momentum, displacement tag, gamma name): [locT] complex}
+        def __init__(self, t0, nt):
+            self.t0, self.nt = t0, nt
+
+        def momentum_loops(self):
+            return {((px, 0, 1), tag, gname): (np.arange(self.t0, self.t0 + self.nt) + 10 * px) * (1 + 2j * ig)
+                    for px in (-1, 0) for tag in ("disp_0", "disp_+t_10") for ig, gname in enumerate(("G0", "G15"))}
+
+    path = os.path.join(out_dir, "loops_parallel.h5")
+    h5lite.write_momentum_loops_time_ranks(path, FakeLoop(ts.t0, ts.Tl), rank, world, dist.barrier)
+    if rank == 0:
+        h5lite.write_momentum_loops(os.path.join(out_dir, "loops_serial.h5"), FakeLoop(0, L[3]))
+        ok = ok and open(path, "rb").read() == open(os.path.join(out_dir, "loops_serial.h5"), "rb").read()
+        ok = ok and len(h5min.read(path)) == 8
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
     dist.destroy_process_group()
 
