@@ -60,53 +60,41 @@ template <typename F, int ND, int UL, int NATIVE>
 __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx<F> &c, const Cplx<F> (&W)[3][3],
                                           Cplx<F> (&M)[4][4], F (&Md)[4], Cplx<F> (&Mo)[6], const bool opposite) {
   // producer side: the warps take turns - warp (m mod nActive) issues ALL bulk copies of eigenvector m's stage (lane i
-  // issues copy i), the others only advance their cursors.  Issuing costs ~100 non-FP64 instructions, which on this
-  // chip are paid in FP64 issue slots; spread over the warps in turn it is ~15 per warp and eigenvector instead of ~65
-  // when every warp issued its own share every time.
+  // issues copy i).  Issuing costs ~100 non-FP64 instructions, which on this chip are paid in FP64 issue slots; spread
+  // over the warps in turn it is ~15 per warp and eigenvector.  Everything the producer needs (stage, barrier, phase) is
+  // derived from m when a warp's turn comes, so the other iterations carry no producer state at all: the loop body is
+  // 390 FP64 + ~55 other instructions (24 operand loads, one barrier wait, one arrive, eight address updates).
   uint32_t total_tx = 0;
   for (int i = 0; i < c.st->ncp; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
   const int lead = c.lane == 0;
   const uint32_t stages_u32 = smem_u32(c.stages);
-  const uint32_t full_u32 = smem_u32(c.full), empty_u32 = smem_u32(c.empty);
+  const uint32_t bar_u32 = smem_u32(c.full);  // full[s] at bar_u32 + 8 s, empty[s] 64 bytes further
   const int ring_bytes = c.S * c.stage_bytes;
   // distance between the colours of one spin: adjacent complex numbers (site-major), or component rows of a chunk of
   // 8 sites (QUDA FLOAT2 stage, [chunk][component][8 sites])
   constexpr int kC = NATIVE ? kChunk * 2 * (int)sizeof(F) : 2 * (int)sizeof(F);
 
-  uint32_t p_full = full_u32, p_empty = empty_u32, p_dst = stages_u32;  // producer cursor (stage of the next issue)
-  int p_left = c.S;                                                      // stages until the cursor wraps
-  uint32_t p_par = 1;  // parity to wait for on the empty barrier; the first pass over the ring does not wait
-  int turn = c.warp;   // issues when it reaches 0
-  auto issue_share = [&](int m, bool wait) {
-    if (turn == 0) {  // warp-uniform
-      if (wait) mbar_wait_u32(p_empty, p_par);
-      const char *ev = static_cast<const char *>(A.vt.evec[m]);
-      mbar_expect_tx_if(p_full, total_tx, lead);
-      if (NATIVE) {  // ev: this eigenvector's three tensor maps (boxes of 1, 2, 4 chunks) in device memory
-        for (int i = c.lane; i < c.st->ncp; i += 32) {
-          const int d = c.st->cp_goff16[i];
-          tma_tensor4_g2s(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((d >> 29) & 3) * 128, d & 0x0fffffff, (d >> 28) & 1, p_full);
-        }
-      } else {
-        for (int i = c.lane; i < c.st->ncp; i += 32)
-          tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4),
-                          (uint32_t)c.st->cp_bytes[i], p_full, 1);
+  auto issue = [&](int m) {  // the whole stage of eigenvector m; warp-uniform
+    const int rev = m / c.S, sm = m - rev * c.S;  // revolution of the ring, stage
+    const uint32_t p_full = bar_u32 + 8u * (uint32_t)sm, p_dst = stages_u32 + (uint32_t)(sm * c.stage_bytes);
+    if (rev > 0) mbar_wait_u32(p_full + 64, (uint32_t)((rev - 1) & 1));  // its previous tenant has been consumed
+    const char *ev = static_cast<const char *>(A.vt.evec[m]);
+    mbar_expect_tx_if(p_full, total_tx, lead);
+    if (NATIVE) {  // ev: this eigenvector's three tensor maps (boxes of 1, 2, 4 chunks) in device memory
+      for (int i = c.lane; i < c.st->ncp; i += 32) {
+        const int d = c.st->cp_goff16[i];
+        tma_tensor4_g2s(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((d >> 29) & 3) * 128, d & 0x0fffffff, (d >> 28) & 1, p_full);
       }
-      turn = c.nActive;
-    }
-    turn--;
-    p_full += 8;
-    p_empty += 8;
-    p_dst += (uint32_t)c.stage_bytes;
-    if (--p_left == 0) {
-      p_left = c.S;
-      p_full = full_u32;
-      p_empty = empty_u32;
-      p_dst = stages_u32;
-      p_par ^= 1u;
+    } else {
+      for (int i = c.lane; i < c.st->ncp; i += 32)
+        tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4),
+                        (uint32_t)c.st->cp_bytes[i], p_full, 1);
     }
   };
-  for (int m = 0; m < c.ahead && m < c.nvec; m++) issue_share(m, false);  // ahead < S: no tenant to wait for
+  for (int m = c.warp; m < c.ahead && m < c.nvec; m += c.nActive) issue(m);  // ahead < S: no tenant to wait for
+  // iteration n refills the ring with eigenvector n + ahead; it is this warp's turn when (n + ahead) mod nActive == warp
+  int until = (c.warp - c.ahead) % c.nActive;
+  if (until < 0) until += c.nActive;
 
   // consumer cursor: absolute shared addresses of the 4 rotated spin blocks of v(x) and v(x+d) in the current stage
   const char *a_own[4], *a_nbr[4];
@@ -115,13 +103,16 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
     a_own[b] = c.stages + c.own_sp[b];
     a_nbr[b] = c.stages + c.nbr_sp[b];
   }
-  uint32_t c_full = full_u32, c_empty = empty_u32;
+  uint32_t c_bar = bar_u32;
   int c_left = c.S;
   uint32_t c_par = 0;
-  const int n_issue = c.nvec - c.ahead;  // iterations that still have a stage to issue
   for (int n = 0; n < c.nvec; n++) {
-    if (n < n_issue) issue_share(n + c.ahead, n + c.ahead >= c.S);
-    mbar_wait_u32(c_full, c_par);
+    if (until == 0) {
+      until = c.nActive;
+      if (n + c.ahead < c.nvec) issue(n + c.ahead);
+    }
+    until--;
+    mbar_wait_u32(c_bar, c_par);
     const F is = (F)A.vt.inv_sigma[n];
     Cplx<F> vp[12];
     if (ND > 0) {
@@ -139,7 +130,7 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
       for (int be = 0; be < 4; be++) lc[be] = lds_c<F>(a_own[be] + cc * kC);
       if (cc == 2) {  // last shared-memory read of this stage: hand it back before the remaining FMAs
         __syncwarp();
-        mbar_arrive_if(c_empty, lead);
+        mbar_arrive_if(c_bar + 64, lead);
       }
       // (1/sigma) v(x): one scaling serves the displaced and the ultra-local accumulation
       Cplx<F> ls[4];
@@ -175,8 +166,7 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
       }
     }
     // next stage: the eight running addresses move on (one add each instead of recomputing base + offset)
-    c_full += 8;
-    c_empty += 8;
+    c_bar += 8;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       a_own[b] += c.stage_bytes;
@@ -184,8 +174,7 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
     }
     if (--c_left == 0) {
       c_left = c.S;
-      c_full = full_u32;
-      c_empty = empty_u32;
+      c_bar = bar_u32;
       c_par ^= 1u;
 #pragma unroll
       for (int b = 0; b < 4; b++) {
