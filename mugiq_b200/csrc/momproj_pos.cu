@@ -185,13 +185,16 @@ momproj_pos_dmma_kernel(double *__restrict__ partial, const double *__restrict__
     }
 }
 
-// SIMT version (FP32): block = (t, iL, parity, chunk), threads stride the K chunk (coalesced); per gamma and momentum a
-// block reduction.  Not a headline path.
+// SIMT version (FP32; the reference has cublasCgemm, lib/loop_mugiq.cpp:371-377): block = (t, iL, parity, chunk).  The
+// threads stride the K chunk (coalesced); each holds the 16 gammas x 4 momenta of its sites in registers, so the dataPos
+// operand is read once per group of four momenta; the 128 partial results of a group are reduced across lanes by shuffles
+// and across the four warps by 128 threads in parallel.
 template <typename F>
 __global__ void __launch_bounds__(128)
 momproj_pos_simt_kernel(F *__restrict__ partial, const F *__restrict__ pos, const F *__restrict__ P, const PosGeom pg) {
   constexpr GammaTables gt = gamma_tables();
-  __shared__ F red[4][2];
+  constexpr int NT = 4;
+  __shared__ F red[4][16 * NT * 2];
   const long long task = blockIdx.x;
   const int chunk = (int)(task % pg.nchunk);
   const int p = (int)((task / pg.nchunk) & 1);
@@ -199,37 +202,54 @@ momproj_pos_simt_kernel(F *__restrict__ partial, const F *__restrict__ pos, cons
   const int t = (int)(pair % pg.Lt), iL = (int)(pair / pg.Lt);
   const int s = (t + p) & 1;
   const int kbeg = chunk * pg.kchunk, kend = min(pg.V3h, kbeg + pg.kchunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   F *out = partial + 2 * (size_t)(p * pg.nchunk + chunk) * (size_t)pg.M * pg.N;
-  for (int G = 0; G < 16; G++) {
-    const F *arow = pos + 2 * (((long long)p * pg.Vh + (long long)t * pg.V3h) + pg.V4 * (G + 16LL * iL));
-    for (int n = 0; n < pg.N; n++) {
-      const F *prow = P + 2 * (((long long)s * pg.N + n) * pg.V3h);
-      Cplx<F> acc = make_c<F>(0, 0);
-      for (int k = kbeg + threadIdx.x; k < kend; k += blockDim.x) cmac(acc, ldg_c<F>(arow + 2 * k), ldg_c<F>(prow + 2 * k));
+  const F *arow0 = pos + 2 * (((long long)p * pg.Vh + (long long)t * pg.V3h) + pg.V4 * (16LL * iL));
+  for (int n0 = 0; n0 < pg.N; n0 += NT) {
+    Cplx<F> acc[16][NT];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        acc.re += __shfl_xor_sync(0xffffffffu, acc.re, off);
-        acc.im += __shfl_xor_sync(0xffffffffu, acc.im, off);
+    for (int G = 0; G < 16; G++)
+#pragma unroll
+      for (int j = 0; j < NT; j++) acc[G][j] = make_c<F>(0, 0);
+    for (int k = kbeg + threadIdx.x; k < kend; k += blockDim.x) {
+      Cplx<F> ph[NT];
+#pragma unroll
+      for (int j = 0; j < NT; j++)
+        ph[j] = n0 + j < pg.N ? ldg_c<F>(P + 2 * (((long long)s * pg.N + n0 + j) * pg.V3h + k)) : make_c<F>(0, 0);
+#pragma unroll
+      for (int G = 0; G < 16; G++) {
+        const Cplx<F> a = ldg_c<F>(arow0 + 2 * (pg.V4 * (long long)G + k));
+#pragma unroll
+        for (int j = 0; j < NT; j++) cmac(acc[G][j], a, ph[j]);
       }
-      if ((threadIdx.x & 31) == 0) {
-        red[threadIdx.x >> 5][0] = acc.re;
-        red[threadIdx.x >> 5][1] = acc.im;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        F re = 0, im = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
-          re += red[w][0];
-          im += red[w][1];
-        }
-        const long long m = t + (long long)pg.Lt * (gt.map_index[G] + 16 * iL);
-        const F sg = (F)gt.map_sign[G];
-        out[2 * (m + pg.M * n)] = sg * re;
-        out[2 * (m + pg.M * n) + 1] = sg * im;
-      }
-      __syncthreads();
     }
+#pragma unroll
+    for (int G = 0; G < 16; G++)
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        Cplx<F> v = acc[G][j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          v.re += __shfl_xor_sync(0xffffffffu, v.re, off);
+          v.im += __shfl_xor_sync(0xffffffffu, v.im, off);
+        }
+        if (lane == 0) {
+          red[warp][(G * NT + j) * 2] = v.re;
+          red[warp][(G * NT + j) * 2 + 1] = v.im;
+        }
+      }
+    __syncthreads();
+    {  // one output number per thread: (G, j, re/im) summed over the four warps, gamma map applied
+      const int o = threadIdx.x, G = o / (NT * 2), j = (o >> 1) % NT, comp = o & 1;
+      if (n0 + j < pg.N) {
+        const F v = red[0][o] + red[1][o] + red[2][o] + red[3][o];
+        const long long m = t + (long long)pg.Lt * ((15 - G) + 16 * iL);
+        out[2 * (m + pg.M * (n0 + j)) + comp] = ((kMapMinusMask >> G) & 1) ? -v : v;
+      }
+    }
+    __syncthreads();
   }
+  (void)gt;
 }
 
 template <typename F>
