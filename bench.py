@@ -879,7 +879,7 @@ def main():
                          "an SM push kernel (kernel), or NCCL send/recv through staging buffers (nccl)")
     ap.add_argument("--tsplit-batch", type=int, default=100, help="--tsplit: eigenvectors per halo push / kernel launch (the push "
                                                                   "of batch i+1 overlaps the kernels of batch i)")
-    ap.add_argument("--tsplit-nev", type=int, default=100, help="eigenvectors per GPU of the `tsplit` object (34 GB of slabs)")
+    ap.add_argument("--tsplit-nev", type=int, default=200, help="eigenvectors per GPU of the `tsplit` object (68 GB of slabs)")
     ap.add_argument("--config4-nev", type=int, default=0, help="eigenvectors per GPU of the `config4` object (default 125)")
     ap.add_argument("--allreduce-chunks", type=int, default=8, help="time-slice chunks of the overlapped position-space all-reduce")
     ap.add_argument("--no-e2e", action="store_true")
