@@ -355,6 +355,11 @@ int mugiq_b200_prof_num_kernels(void);
 const char *mugiq_b200_prof_name(int kernel_id);
 int mugiq_b200_prof_query(int kernel_id, long long *launches, long long *timed_launches, double *ms_total,
                           double *alg_bytes_total, double *alg_flops_total);
+/* Per-CTA timeline of the fused kernel (diagnostics): while trace_d != NULL every CTA b < capacity_ctas of
+ * the following fused launches writes 16 long long to trace_d[16 b]: SM id, then %globaltimer (ns) at CTA start, stage map
+ * ready, eigenvector loop entered, loop left, CTA end, two spare; the SM's clock64 at the same marks in [9..13].  NULL
+ * switches it off (one predicated store per mark). */
+int mugiq_b200_prof_fused_trace(void *trace_d, long long capacity_ctas);
 
 #ifdef __cplusplus
 }

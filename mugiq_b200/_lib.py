@@ -100,6 +100,7 @@ SYMBOLS = {
     "mugiq_b200_prof_num_kernels": (_i, []),
     "mugiq_b200_prof_name": (C.c_char_p, [_i]),
     "mugiq_b200_prof_query": (_i, [_i, C.POINTER(_ll), C.POINTER(_ll), _pd, _pd, _pd]),
+    "mugiq_b200_prof_fused_trace": (_i, [_vp, _ll]),
 }
 
 _lib = None

@@ -12,6 +12,8 @@ constexpr int kFusedMaxIv = 64;      // merged intervals (= bulk copies) of one 
 // per thread (a third warp would cap the kernel at 168 and spill the 4x4 spin matrix + link + operands)
 constexpr int kFusedComputeWarps = 8;
 constexpr int kFusedThreads = kFusedComputeWarps * 32;
+// warp-specialised form: one more warp group (4 warps, setmaxnreg works per warp group) whose first warp is the TMA producer
+constexpr int kFusedThreadsWS = kFusedThreads + 128;
 
 // One displaced loop of a launch group: the kernel computes  M(x) += (1/sigma) conj(v(x)) (x) [W(x) v(x + sign*len*dir)]
 // where W is the Wilson line of `len` links (already daggered / shifted for minus), stored like one direction
@@ -50,6 +52,9 @@ int fused_max_loops_per_group(const LatGeom &g, int precision);
 // eigenvectors over the sites of the time-slices [t_begin, t_end) (the whole lattice for 0, Lt): a rank of a lattice-T split computes its interior only and merely READS the halo slices.
 int fused_group_launch(void *dataPos_d, const FusedGroup &grp, long long ul_off, const FusedVecTable &vt, int accumulate,
                        const LatGeom &g, int precision, cudaStream_t stream, int t_begin = 0, int t_end = -1);
+
+// per-CTA timeline of the following launches (diagnostics; nullptr switches it off)
+void fused_set_trace(long long *trace_d, long long capacity_ctas);
 
 // host-only self-check of the tiling of one launch group (fused_kernel.cu); out = {run, units, nstages, stage_bytes,
 // max copies per stage, mean sites staged per CTA, sites not found in their stage, malformed stage maps}

@@ -54,6 +54,27 @@
 
 namespace mugiq_b200 {
 
+// per-CTA timeline (mugiq_b200_prof_fused_trace): thread 0 stamps %globaltimer at the marks of the kernel
+static long long *g_fused_trace = nullptr;
+static int g_fused_trace_ctas = 0;
+void fused_set_trace(long long *trace_d, long long capacity_ctas) {
+  g_fused_trace = trace_d;
+  g_fused_trace_ctas = trace_d ? (int)std::min<long long>(capacity_ctas, 1 << 30) : 0;
+}
+template <typename F> __device__ __forceinline__ void trace_mark(const FusedArgs<F> &A, int slot) {
+  if (A.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x < A.trace_ctas) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    A.trace[16 * (size_t)blockIdx.x + slot] = (long long)t;
+    A.trace[16 * (size_t)blockIdx.x + 8 + slot] = clock64();
+    if (slot == 1) {
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      A.trace[16 * (size_t)blockIdx.x] = sm;
+    }
+  }
+}
+
 // The eigenvector loop of one role: ND displaced loops in the group, this thread works on one of them and on its
 // share of the ultra-local entries.
 template <typename F, int ND, int UL, int NATIVE>
@@ -185,8 +206,161 @@ __device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx
   }
 }
 
-template <typename F, int ND, int NATIVE>
-__global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __grid_constant__ FusedArgs<F> A) {
+// ---- warp-specialised form (WS = 1, the default) -----------------------------------------------------------------------------
+// Measured on B200 (tools/issue_bench.cu, tools/fused_trace.py, ncu instruction samples): a warp issues one
+// DFMA per 4 cycles whether or not its SM sub-partition's other warp competes, and two warps exactly fill the FP64 pipe - so
+// everything a compute warp does besides its 390 FP64 instructions per eigenvector is serial time of that warp and idles the
+// pipe.  Integer / uniform instructions are almost free (they issue in the shadow of a DFMA), LDS costs ~4 cycles, a barrier
+// try_wait whose result is consumed at once ~50 cycles, and the turn-taking TMA issue of the round-2 loop ~200-260 cycles per
+// eigenvector.  Hence: a PRODUCER warp (its own warp group, registers handed to the compute warps with setmaxnreg) issues every
+// bulk copy and waits for the empty barriers; the compute warps only test the full barrier of the NEXT stage half an
+// eigenvector ahead (non-blocking mbarrier.test_wait) and consume.
+__device__ __forceinline__ uint32_t mbar_test_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok;
+}
+
+template <typename F, int NATIVE>
+__device__ __forceinline__ void producer_loop(const FusedArgs<F> &A, const StageMap &st, uint32_t stages_u32, uint32_t bar_u32, int S,
+                                              int stage_bytes, int lane) {
+  uint32_t total_tx = 0;
+  for (int i = 0; i < st.ncp; i++) total_tx += (uint32_t)st.cp_bytes[i];
+  const int lead = lane == 0;
+  const int nvec = A.vt.nvec;
+  int sm = 0;           // stage of eigenvector m
+  uint32_t par = 1;     // parity of the empty barrier's phase BEFORE its first completion: the first S waits pass at once
+  for (int m = 0; m < nvec; m++) {
+    const uint32_t p_full = bar_u32 + 8u * (uint32_t)sm, p_dst = stages_u32 + (uint32_t)(sm * stage_bytes);
+    mbar_wait_u32(p_full + 64, par);  // the stage's previous tenant has been consumed by every compute warp
+    const char *ev = static_cast<const char *>(A.vt.evec[m]);
+    mbar_expect_tx_if(p_full, total_tx, lead);
+    if (NATIVE) {  // ev: this eigenvector's three tensor maps (boxes of 1, 2, 4 chunks) in device memory
+      for (int i = lane; i < st.ncp; i += 32) {
+        const int d = st.cp_goff16[i];
+        tma_tensor4_g2s(p_dst + (uint32_t)st.cp_soff[i], ev + ((d >> 29) & 3) * 128, d & 0x0fffffff, (d >> 28) & 1, p_full);
+      }
+    } else {
+      for (int i = lane; i < st.ncp; i += 32)
+        tma_bulk_g2s_if(p_dst + (uint32_t)st.cp_soff[i], ev + ((size_t)st.cp_goff16[i] << 4), (uint32_t)st.cp_bytes[i], p_full, 1);
+    }
+    if (++sm == S) {
+      sm = 0;
+      par ^= 1u;
+    }
+  }
+}
+
+template <typename F, int ND, int UL, int NATIVE>
+__device__ __forceinline__ void consumer_loop(const FusedArgs<F> &A, const ThreadCtx<F> &c, const Cplx<F> (&W)[3][3],
+                                              Cplx<F> (&M)[4][4], F (&Md)[4], Cplx<F> (&Mo)[6]) {
+  const int lead = c.lane == 0;
+  const uint32_t bar_u32 = smem_u32(c.full);  // full[s] at bar_u32 + 8 s, empty[s] 64 bytes further
+  const int ring_bytes = c.S * c.stage_bytes;
+  constexpr int kC = NATIVE ? kChunk * 2 * (int)sizeof(F) : 2 * (int)sizeof(F);
+  const char *a_own[4], *a_nbr[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    a_own[b] = c.stages + c.own_sp[b];
+    a_nbr[b] = c.stages + c.nbr_sp[b];
+  }
+  uint32_t c_bar = bar_u32, c_par = 0;
+  int c_left = c.S;
+  uint32_t ok = mbar_test_u32(c_bar, c_par);
+  for (int n = 0; n < c.nvec; n++) {
+    if (!ok) mbar_wait_u32(c_bar, c_par);
+    const F is = (F)A.vt.inv_sigma[n];
+    Cplx<F> vp[12];
+    if (ND > 0) {
+#pragma unroll
+      for (int al = 0; al < 4; al++) {
+        vp[al * 3 + 0] = lds_c<F>(a_nbr[al]);
+        vp[al * 3 + 1] = lds_c<F>(a_nbr[al] + kC);
+        vp[al * 3 + 2] = lds_c<F>(a_nbr[al] + 2 * kC);
+      }
+    }
+    const uint32_t bar_n = c_bar;
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+      Cplx<F> lc[4];
+#pragma unroll
+      for (int be = 0; be < 4; be++) lc[be] = lds_c<F>(a_own[be] + cc * kC);
+      if (cc == 1) {  // look at the next stage's barrier now, use the answer at the top of the next iteration
+        c_bar += 8;
+        if (--c_left == 0) {
+          c_left = c.S;
+          c_bar = bar_u32;
+          c_par ^= 1u;
+        }
+        ok = mbar_test_u32(c_bar, c_par);
+      }
+      if (cc == 2) {  // last shared-memory read of this stage: hand it back before the remaining FMAs
+        __syncwarp();
+        mbar_arrive_if(bar_n + 64, lead);
+      }
+      // 1/sigma rides on the link row (6 multiplications per colour instead of 8 on v(x)); the ultra-local share scales the
+      // entries it needs itself (as they are used: no scaled copy of v(x) is kept, the registers are needed elsewhere)
+      constexpr bool kScaleOwn = ND == 0;
+      Cplx<F> ls[4];
+      if (kScaleOwn) {
+#pragma unroll
+        for (int be = 0; be < 4; be++) ls[be] = make_c<F>(lc[be].re * is, lc[be].im * is);
+      }
+      if (ND > 0) {
+        Cplx<F> Ws[3], Rc[4];
+#pragma unroll
+        for (int k = 0; k < 3; k++) Ws[k] = kScaleOwn ? W[cc][k] : make_c<F>(W[cc][k].re * is, W[cc][k].im * is);
+#pragma unroll
+        for (int al = 0; al < 4; al++) {
+          Rc[al] = cmul(Ws[0], vp[al * 3 + 0]);
+          cmac(Rc[al], Ws[1], vp[al * 3 + 1]);
+          cmac(Rc[al], Ws[2], vp[al * 3 + 2]);
+        }
+#pragma unroll
+        for (int be = 0; be < 4; be++)
+#pragma unroll
+          for (int al = 0; al < 4; al++) cmac_conj(M[be][al], kScaleOwn ? ls[be] : lc[be], Rc[al]);
+      }
+      if (UL == UL_ALL) {
+#pragma unroll
+        for (int be = 0; be < 4; be++) {
+          const Cplx<F> l = kScaleOwn ? ls[be] : make_c<F>(lc[be].re * is, lc[be].im * is);
+          Md[be] = fma(l.re, lc[be].re, Md[be]);
+          Md[be] = fma(l.im, lc[be].im, Md[be]);
+#pragma unroll
+          for (int k = 4; k < 10; k++)
+            if (ul_pair_be(k) == be) cmac_conj(Mo[k - 4], l, lc[ul_pair_al(k)]);
+        }
+      }
+      if (UL == UL_ROT) {
+        const Cplx<F> l0 = make_c<F>(lc[0].re * is, lc[0].im * is);
+        Md[0] = fma(l0.re, lc[0].re, Md[0]);
+        Md[0] = fma(l0.im, lc[0].im, Md[0]);
+        cmac_conj(Mo[0], l0, lc[1]);
+        cmac_conj(Mo[1], l0, lc[2]);  // needed from roles 0 and 1 only; computing it everywhere keeps the code uniform
+      }
+    }
+    // next stage: the eight running addresses move on; c_left already counts the NEXT stage
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      a_own[b] += c.stage_bytes;
+      a_nbr[b] += c.stage_bytes;
+    }
+    if (c_left == c.S) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        a_own[b] -= ring_bytes;
+        a_nbr[b] -= ring_bytes;
+      }
+    }
+  }
+}
+
+template <typename F, int ND, int NATIVE, int WS>
+__global__ void __launch_bounds__(WS ? kFusedThreadsWS : kFusedThreads, 1) loop_fused_kernel(const __grid_constant__ FusedArgs<F> A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);        // [nstages]
   uint64_t *empty = reinterpret_cast<uint64_t *>(smem + 64);  // [nstages]
@@ -196,6 +370,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   F *xch = reinterpret_cast<F *>(smem + kSmemHeader);  // [units*32][16] ultra-local entries, true spin labels
   char *stages = reinterpret_cast<char *>(smem + kSmemHeader + tl.units * 32 * 16 * (int)sizeof(F));
 
+  trace_mark(A, 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_ul = A.ul_off >= 0;
   constexpr int nrole = ND > 0 ? ND : 1;  // a launch without displaced loops runs one pure ultra-local role
@@ -206,15 +381,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   const int c0 = A.c_begin + (int)blockIdx.x * tl.run;
   const int c1 = min(c0 + tl.run, A.c_end);
 
+  if (A.maps != nullptr) {  // this CTA's stage map, worked out once per (lattice, group, range) by stage_maps_kernel
+    const int4 *src = reinterpret_cast<const int4 *>(A.maps + blockIdx.x);
+    int4 *dst = reinterpret_cast<int4 *>(&st);
+    for (int i = threadIdx.x; i < (int)(sizeof(StageMap) / sizeof(int4)); i += blockDim.x) dst[i] = __ldg(src + i);
+  }
   if (threadIdx.x == 0) {
-    build_stage_map(st, A.grp, g, kSite, c0, c1, NATIVE ? kChunk : 1);
+    if (A.maps == nullptr) build_stage_map(st, A.grp, g, kSite, c0, c1, NATIVE ? kChunk : 1);
     for (int s = 0; s < tl.nstages; s++) {
-      mbar_init(&full[s], 1);        // one arrive.expect_tx by the warp whose turn it is
+      mbar_init(&full[s], 1);        // one arrive.expect_tx by the warp that issues the stage
       mbar_init(&empty[s], nActive);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  trace_mark(A, 2);
+  if (WS) {
+    if (warp >= kFusedComputeWarps) {  // producer warp group: keeps 40 registers per thread, one warp works
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == kFusedComputeWarps)
+        producer_loop<F, NATIVE>(A, st, smem_u32(stages), smem_u32(full), tl.nstages, tl.stage_bytes, lane);
+      return;
+    }
+    // 8 x 32 x 232 + 4 x 32 x 40 = 64512 of the 65536 registers of an SM
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  }
 
   const bool active = warp < nActive;
   // ---- role of this thread: displaced loop j (if any) on site c0 + q of parity p -------------------------------
@@ -290,15 +481,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
   }
 
   const int ul_mode = !has_ul ? UL_NONE : (ND == 4 ? UL_ROT : (j == 0 ? UL_ALL : UL_NONE));
+  trace_mark(A, 3);
+  if (WS && A.skew > 0) {  // stagger the compute warps (see consumer_loop): warp w starts w * skew cycles late
+    const long long t0 = clock64();
+    const long long wait = (long long)warp * A.skew;
+    while (clock64() - t0 < wait) {
+    }
+  }
   if (active) {
-    if (ul_mode == UL_NONE)
-      evec_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo, false);
-    else if (ul_mode == UL_ALL)
-      evec_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo, false);
-    else
-      evec_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo, j < 2);
+    if (WS) {
+      if (ul_mode == UL_NONE)
+        consumer_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo);
+      else if (ul_mode == UL_ALL)
+        consumer_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo);
+      else
+        consumer_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo);
+    } else {
+      if (ul_mode == UL_NONE)
+        evec_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo, false);
+      else if (ul_mode == UL_ALL)
+        evec_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo, false);
+      else
+        evec_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo, j < 2);
+    }
   }
 
+  trace_mark(A, 4);
   // ---- epilogue: undo the spin rotation, gamma projection (adds/swaps only), one write of the loop buffer ---------
   const int nid = u * 32 + lane;
   if (has_ul && valid && ul_mode != UL_NONE) {  // publish this thread's share under the true spin labels
@@ -320,8 +528,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
       if (j < 2) put_pair(0, 2, Mo[1]);
     }
   }
-  __syncthreads();
-  if (!valid) return;
+  if (WS)
+    asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");  // the compute warps only (the producer group has left)
+  else
+    __syncthreads();
+  if (!valid) {
+    trace_mark(A, 5);
+    return;
+  }
   if (ND > 0) {
     unrotate_rt<F, true>(M, k_own);
     unrotate_rt<F, false>(M, k_nbr);
@@ -367,6 +581,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) loop_fused_kernel(const __gr
       st_c<F>(po, o);
     }
   }
+  trace_mark(A, 5);
 }
 
 // ---- host side: tiling and launch ----------------------------------------------------------------------------
@@ -410,6 +625,82 @@ static int max_stage_sites(const FusedGroup &grp, const LatGeom &g, int run, int
   }
   *overflow = it->second.second;
   return it->second.first;
+}
+
+// ---- stage maps of a launch, built once on the device ----------------------------------------------------------------------
+// Thread 0 of a CTA needed ~7 us (3 % of a CTA's life at BASELINE configs[1], tools/fused_trace.py) to work out its stage map;
+// the maps depend on (lattice, group geometry, range, run) only, so one small kernel writes them all to device memory the
+// first time a launch shape is seen and every later CTA just copies its 1.8 KB.
+__global__ void stage_maps_kernel(StageMap *out, FusedGroup grp, LatGeom g, int site_bytes, int c_begin, int c_end, int run, int align,
+                                  int ncta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ncta) return;
+  const int c0 = c_begin + b * run;
+  build_stage_map(out[b], grp, g, site_bytes, c0, min(c0 + run, c_end), align);
+}
+
+namespace {
+struct StageMapsEntry {
+  StageMap *dev = nullptr;
+  cudaEvent_t built = nullptr;
+  bool ready = false;
+  size_t bytes = 0;
+};
+struct StageMapsCache {
+  std::mutex mu;
+  std::map<std::vector<int>, StageMapsEntry> entries;
+  size_t bytes = 0;
+};
+StageMapsCache &stage_maps_cache(int dev) {
+  static StageMapsCache c[64];
+  return c[(dev >= 0 && dev < 64) ? dev : 0];
+}
+}  // namespace
+
+static int stage_maps_get(const StageMap **maps, const FusedGroup &grp, const LatGeom &g, int site_bytes, int c_begin, int c_end,
+                          int run, int align, int ncta, cudaStream_t stream) {
+  static_assert(sizeof(StageMap) % sizeof(int4) == 0, "StageMap is copied as int4");
+  int dev = 0;
+  MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
+  StageMapsCache &c = stage_maps_cache(dev);
+  std::vector<int> key = {g.L[0], g.L[1], g.L[2], g.L[3], site_bytes, run, c_begin, c_end, align, grp.nloops};
+  for (int j = 0; j < grp.nloops; j++) {
+    key.push_back(grp.loop[j].dir);
+    key.push_back(grp.loop[j].sign);
+    key.push_back(grp.loop[j].len);
+  }
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.entries.find(key);
+  if (it == c.entries.end()) {
+    const size_t bytes = (size_t)ncta * sizeof(StageMap);
+    if (c.bytes + bytes > ((size_t)2 << 30)) {  // start over: nothing in flight may still read the old maps
+      MUGIQ_CUDA_CHECK(cudaDeviceSynchronize());
+      for (auto &e : c.entries) {
+        cudaFree(e.second.dev);
+        cudaEventDestroy(e.second.built);
+      }
+      c.entries.clear();
+      c.bytes = 0;
+    }
+    StageMapsEntry e;
+    e.bytes = bytes;
+    MUGIQ_CUDA_CHECK(cudaMalloc((void **)&e.dev, bytes));
+    MUGIQ_CUDA_CHECK(cudaEventCreateWithFlags(&e.built, cudaEventDisableTiming));
+    stage_maps_kernel<<<(ncta + 63) / 64, 64, 0, stream>>>(e.dev, grp, g, site_bytes, c_begin, c_end, run, align, ncta);
+    MUGIQ_LAUNCH_CHECK();
+    MUGIQ_CUDA_CHECK(cudaEventRecord(e.built, stream));
+    c.bytes += bytes;
+    it = c.entries.emplace(key, e).first;
+  }
+  StageMapsEntry &e = it->second;
+  if (!e.ready) {  // a launch on another stream must not overtake the builder
+    if (cudaEventQuery(e.built) == cudaSuccess)
+      e.ready = true;
+    else
+      MUGIQ_CUDA_CHECK(cudaStreamWaitEvent(stream, e.built, 0));
+  }
+  *maps = e.dev;
+  return MUGIQ_B200_OK;
 }
 
 // Run length: the CTA's warps = (roles: threads working on one site) x (warps per role), a warp = 32 consecutive sites of
@@ -525,20 +816,28 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
   return -1;
 }
 
-template <typename F, int ND, int NATIVE>
-static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
+template <typename F, int ND, int NATIVE, int WS>
+static int launch_fused_ndp(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
   // the shared-memory opt-in is a per-device function attribute
   static bool attr_set[64];
   int dev = 0;
   MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND, NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND, NATIVE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           fused_smem_limit_bytes()));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  loop_fused_kernel<F, ND, NATIVE><<<grid, kFusedThreads, smem, stream>>>(args);
+  loop_fused_kernel<F, ND, NATIVE, WS><<<grid, WS ? kFusedThreadsWS : kFusedThreads, smem, stream>>>(args);
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
+}
+template <typename F, int ND, int NATIVE>
+static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
+  static const int ws = [] {  // MUGIQ_B200_FUSED_WS=0: the round-2 kernel (compute warps take turns issuing the copies)
+    const char *e = getenv("MUGIQ_B200_FUSED_WS");
+    return e ? atoi(e) : 1;
+  }();
+  return ws ? launch_fused_ndp<F, ND, NATIVE, 1>(args, smem, grid, stream) : launch_fused_ndp<F, ND, NATIVE, 0>(args, smem, grid, stream);
 }
 
 template <typename F>
@@ -551,6 +850,14 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   args.ul_off = ul_off;
   args.dataPos = static_cast<F *>(dataPos_d);
   args.accumulate = accumulate;
+  args.maps = nullptr;
+  static const int skew = [] {
+    const char *e = getenv("MUGIQ_B200_FUSED_SKEW");
+    return e ? atoi(e) : 0;
+  }();
+  args.skew = skew;
+  args.trace = g_fused_trace;
+  args.trace_ctas = g_fused_trace_ctas;
   // time-slice range -> range of checkerboard indices (a time-slice is V3/2 consecutive sites of each parity)
   const int V3h = g.V3 / 2;
   args.c_begin = t_begin * V3h;
@@ -559,6 +866,15 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
   const int grid = (args.c_end - args.c_begin + args.tl.run - 1) / args.tl.run;
+  static const bool premap = [] {  // MUGIQ_B200_FUSED_PREMAP=0: every CTA builds its own stage map (round 2)
+    const char *e = getenv("MUGIQ_B200_FUSED_PREMAP");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (premap) {
+    const int rc = stage_maps_get(&args.maps, grp, g, 24 * (int)sizeof(F), args.c_begin, args.c_end, args.tl.run, vt.native ? kChunk : 1,
+                                  grid, stream);
+    if (rc != MUGIQ_B200_OK) return rc;
+  }
   const double frac = (double)(t_end - t_begin) / (double)g.L[3];  // share of the lattice this launch computes
   const size_t smem =
       kSmemHeader + (size_t)args.tl.units * 32 * 16 * sizeof(F) + (size_t)args.tl.nstages * args.tl.stage_bytes;

@@ -230,6 +230,10 @@ template <typename F> struct FusedArgs {
   F *dataPos;
   long long ul_off;    // complex offset of the ultra-local loop's block in dataPos, < 0: not in this launch
   int accumulate;
+  const StageMap *maps;  // stage map of every CTA of the launch (device memory), or NULL: thread 0 of a CTA builds its own
+  long long *trace;    // per-CTA timeline (mugiq_b200_prof_fused_trace), normally NULL
+  int trace_ctas;
+  int skew;            // compute warp w enters the eigenvector loop w * skew cycles late (0: all at once)
   int c_begin, c_end;  // checkerboard-index range [c_begin, c_end) of both parities this launch computes: the time-slices
                        // [t_begin, t_end) of a lattice-T split slab, or the whole lattice
 };

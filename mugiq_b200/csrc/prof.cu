@@ -2,6 +2,7 @@
 #include <mutex>
 #include <vector>
 
+#include "fused.cuh"
 #include "kernels.cuh"
 #include "prof.cuh"
 
@@ -117,6 +118,12 @@ int mugiq_b200_prof_query(int kernel_id, long long *launches, long long *timed_l
   if (ms_total) *ms_total = s.ms[kernel_id];
   if (alg_bytes_total) *alg_bytes_total = s.bytes[kernel_id];
   if (alg_flops_total) *alg_flops_total = s.flops[kernel_id];
+  return MUGIQ_B200_OK;
+}
+
+int mugiq_b200_prof_fused_trace(void *trace_d, long long capacity_ctas) {
+  if (trace_d && capacity_ctas < 1) return set_error(MUGIQ_B200_EINVAL, "mugiq_b200_prof_fused_trace: capacity %lld", capacity_ctas);
+  fused_set_trace(static_cast<long long *>(trace_d), capacity_ctas);
   return MUGIQ_B200_OK;
 }
 

@@ -540,6 +540,14 @@ def prof_reset():
     check(_lib.load().mugiq_b200_prof_reset())
 
 
+def prof_fused_trace(buf=None):
+    """Per-CTA timeline of the following fused launches into `buf` (int64 CUDA tensor, 16 per CTA); None switches it off."""
+    if buf is None:
+        check(_lib.load().mugiq_b200_prof_fused_trace(None, 0))
+    else:
+        check(_lib.load().mugiq_b200_prof_fused_trace(C.c_void_p(buf.data_ptr()), buf.numel() // 16))
+
+
 def prof_report():
     """{kernel name: {"launches", "timed", "ms", "alg_bytes"}} for every kernel launched since the last reset."""
     lib = _lib.load()
