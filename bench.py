@@ -76,6 +76,17 @@ def fp64_peaks():
                          "(profiles/r1_fp64_gemm_peak.json)"}
     except Exception:
         pass
+    # round 3: cycles per DFMA of the operand patterns (tools/dfma_bench.cu).  The fused kernel's FMAs are complex 4x4
+    # outer products (two fresh 64-bit register operands per instruction): that stream tops out below the chained one
+    try:
+        with open(os.path.join(ROOT, "profiles", "r3_dfma_bench.json")) as fh:
+            db = json.load(fh)
+        out["dfma_cplx_outer_tflops"] = db["cplx_outer4x4_8warps"]["tflops"]
+        out["dfma_cplx_outer_sustained_tflops"] = db.get("cplx_outer4x4_sustained_6s", {}).get("tflops")
+        out["dfma_cplx_outer_cycles"] = db["cplx_outer4x4_8warps"]["cycles_per_dfma_per_smsp"]
+        out["dfma_chain_cycles"] = db["chain_8warps"]["cycles_per_dfma_per_smsp"]
+    except Exception:
+        pass
     return out
 
 
@@ -473,6 +484,14 @@ def roofline_of(report, ms_step, steps, nmom):
                 "peak_source": fpk["source"] + "; the driver's MEASURED_PEAKS.json holds no FP64 figure",
                 "frac_of_dmma_stream": tf / fpk["dmma_tflops"], "frac_of_cublas_zgemm": tf / fpk["zgemm_4096_tflops"],
                 "flop_per_algorithmic_byte": intensity, "ridge_flop_per_byte": ridge}
+        if fpk.get("dfma_cplx_outer_tflops"):
+            # the kernel's own instruction pattern as a bare register stream (tools/dfma_bench.cu, same 8 warps per SM): what
+            # the FP64 pipe delivers for complex outer products, 2.52 cycles per DFMA against 2.22 for a chained stream
+            fp64["frac_of_cplx_outer_product_stream"] = tf / fpk["dfma_cplx_outer_tflops"]
+            fp64["cplx_outer_product_stream"] = {"tflops": fpk["dfma_cplx_outer_tflops"],
+                                                 "cycles_per_dfma": fpk.get("dfma_cplx_outer_cycles"),
+                                                 "chained_stream_cycles_per_dfma": fpk.get("dfma_chain_cycles"),
+                                                 "source": "tools/dfma_bench.cu (profiles/r3_dfma_bench.json)"}
         if intensity > ridge:
             # FP64-pipe bound: the headline roofline is the FP64 one; the HBM figures stay beside it
             roof = {"bound": "fp64", "kernel": dom, "achieved": tf, "peak": fpk["dfma_tflops"], "unit": "TFLOP/s",
@@ -831,12 +850,16 @@ def run_ours(args, wl, name):
                          "NVLink (%d-sided eigenvector halo of %d slice(s), transport %s; interior-only compute)"
                          % (L[3] * world, ts.H, nev * ts.halo_bytes_per_vector(slices=halo_slices) / 1e6, halo_sides,
                             halo_slices, args.halo))
+        clk = sampler.summary()
+        if roofline and roofline.get("bound") == "fp64" and clk.get("sm_mhz") and clk.get("sm_max_mhz"):
+            # under the board's power cap a long FP64 step runs below the maximum SM clock: the same fraction per cycle
+            roofline["fp64"]["frac_clock_normalised"] = roofline["fp64"]["frac"] * clk["sm_max_mhz"] / clk["sm_mhz"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": make_config(name, wl, nev, world, args.evec_batch, partition),
                 "roofline": roofline, "verified": verified["ok"] if verified else None, "verification": verified,
                 "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "e2e_cpp": e2e_cpp, "quda_order": quda,
-                "config4": config4, "tsplit": tsplit_obj, "gpu_launches": launches, "clocks": sampler.summary()}
+                "config4": config4, "tsplit": tsplit_obj, "gpu_launches": launches, "clocks": clk}
         OUT.emit(line)
     h.close()
     return 0

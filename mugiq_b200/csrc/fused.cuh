@@ -72,8 +72,17 @@ int wilson_extend(void *Wout_d, const void *Win_d, const void *gauge_d, int dir,
 // Wminus(x) = [Wplus(x - len*dir)]^dagger
 int wilson_minus_from_plus(void *Wminus_d, const void *Wplus_d, int dir, int len, const LatGeom &g, int precision,
                            cudaStream_t stream);
-// loopMinus[G][x] (+)= herm(G) * conj(loopPlus[G][x - len*dir])   (Gamma_G^dagger = herm(G) Gamma_G)
-int loop_minus_from_plus(void *minus_d, const void *plus_d, int dir, int len, int accumulate, const LatGeom &g,
-                         int precision, cudaStream_t stream);
+// loopMinus[G][x] (+)= herm(G) * conj(loopPlus[G][x - len*dir])   (Gamma_G^dagger = herm(G) Gamma_G), for up to
+// kMinusBatch (plus slot, minus slot) pairs of the loop buffer in one launch
+constexpr int kMinusBatch = 32;
+struct MinusBatch {
+  struct Item {
+    int dst, src, dir, len;  // loop slots of dataPos
+  };
+  Item item[kMinusBatch];
+  int n;
+};
+int loop_minus_from_plus(void *dataPos_d, const MinusBatch &batch, int accumulate, const LatGeom &g, int precision,
+                         cudaStream_t stream);
 
 }  // namespace mugiq_b200

@@ -11,29 +11,28 @@
 // A displacement of length k is applied as one Wilson-line multiplication W_k(x) v(x + k mu) (wilson.cu
 // builds W_k from the links once per gauge field), so no displaced eigenvector is ever written to memory.
 //
-// Design ("kernels"; the numbers quoted are measured on B200, profiles/):
-//  * The kernel is FP64-FMA bound (B200: 34 TFLOP/s measured, DMMA shares the pipe): 360 DFMA/DMUL per
-//    (eigvec, site, displaced loop) + ~30 for the share of the ultra-local matrix, against 192 B of compulsory
-//    HBM traffic per (eigvec, site).  Everything else is arranged so that the FP64 pipe is the only busy unit:
-//    on this chip every other instruction takes FP64 issue slots (one IMAD per DFMA halves the DFMA rate,
-//    tools/microbench.cu), so the loop body is ~390 FP64 + ~175 other instructions per eigenvector.
+// Design (the numbers quoted are measured on B200, profiles/):
+//  * The kernel is FP64-pipe bound: 360 DFMA/DMUL per (eigvec, site, displaced loop) + ~30 for the share of the ultra-local
+//    matrix, against 192 B of compulsory HBM traffic per (eigvec, site).  What the pipe delivers depends on the operands: a
+//    chained stream (two operands shared by all instructions) issues one DFMA per 2.22 cycles and SM sub-partition, the
+//    complex 4x4 outer products of this kernel (two fresh 64-bit register operands per instruction) one per 2.52 cycles
+//    (tools/dfma_bench.cu); the eigenvector loop runs at 2.6.  Integer / uniform instructions issue in the shadow of the
+//    DFMAs and are almost free, an LDS.128 costs ~4 cycles of its warp, a barrier wait whose result is consumed at once ~50
+//    (tools/issue_bench.cu) - which is why the compute warps do nothing but load, multiply and release (see below).
 //  * CTA tile = a RUN of 32*k consecutive checkerboard sites [c0, c0 + run) of BOTH parities (k = 1 with 3 or 4
 //    displaced loops in the group).  In the even/odd site-major layout a lattice row (all x at fixed y,z,t) is two
 //    contiguous half-rows (one per parity) of Lx/2 sites x 192 B and rows consecutive in y are contiguous, so for
 //    Lx/2 = 8, 16, 32 a run is 4, 2, 1 whole rows; for Lx/2 = 12, 24 (24^3x48, 48^3x96) it is a fractional number of
-//    rows and still fills every lane of every warp (whole-row tiles left 8 of 32 lanes idle there).  What a stage
-//    holds per eigenvector is a union of INTERVALS of checkerboard-index space: the run itself, and for every loop of
-//    the group the image of each row piece of the run under the shift (y, z, t shifts move a piece to another row of
-//    the opposite or same parity; an x shift of length k needs the piece widened by ceil(k/2) sites, wrapped inside
-//    its row).  Overlapping and adjoining intervals are merged, so every interval is ONE bulk-TMA copy
-//    (cp.async.bulk + mbarrier complete_tx; small copies cost ~100-500 cycles each, tools/tma_bench.cu) and shared
-//    sites (the +y image of a run overlaps the run) are fetched once.  Layout in shared memory is dense:
-//    [interval][site][12 complex].
-//  * 8 warps (2 per SM sub-partition -> 255 registers per thread, no spills): warp = (loop, parity-half of the
-//    tile), thread = (site, loop) and owns the 4x4 complex spin matrix M (32 doubles), the 3x3 link W (18) and its
-//    share of the Hermitian ultra-local matrix for the whole batch.  Every warp issues its share of the TMA copies
-//    S-2 stages ahead (full/empty mbarrier ring), so there is no dedicated producer warp and no block barrier in
-//    the eigenvector loop.
+//    rows and still fills every lane of every warp.  What a stage holds per eigenvector is a union of INTERVALS of
+//    checkerboard-index space: the run itself, and for every loop of the group the image of each row piece of the run
+//    under the shift.  Overlapping and adjoining intervals are merged, so every interval is ONE bulk-TMA copy
+//    (cp.async.bulk + mbarrier complete_tx) and shared sites are fetched once.  Layout in shared memory is dense:
+//    [interval][site][12 complex].  The stage maps of all CTAs of a launch shape are built once on the device
+//    (stage_maps_kernel) and cached; a CTA copies its 1.8 KB.
+//  * 12 warps: 8 compute warps (2 per SM sub-partition; 232 registers each after setmaxnreg) + a producer warp group of
+//    which one warp issues every bulk copy of every stage and waits for the empty barriers (40 registers).  Compute warp =
+//    (loop, parity-half of the tile), thread = (site, loop); it owns the 4x4 complex spin matrix M (32 doubles), the 3x3 link
+//    W (18) and its share of the Hermitian ultra-local matrix for the whole batch.  No block barrier in the eigenvector loop.
 //  * Bank conflicts: 192-B site stride means lanes reading the same component hit only two 16-B bank groups.
 //    Instead of padding (which would forbid multi-row bulk copies) each lane reads its site with the spin index
 //    rotated by k = (lane/2) mod 4, i.e. it keeps spin (b+k) mod 4 in register slot b.  The 8 lanes of a
@@ -75,146 +74,16 @@ template <typename F> __device__ __forceinline__ void trace_mark(const FusedArgs
   }
 }
 
-// The eigenvector loop of one role: ND displaced loops in the group, this thread works on one of them and on its
-// share of the ultra-local entries.
-template <typename F, int ND, int UL, int NATIVE>
-__device__ __forceinline__ void evec_loop(const FusedArgs<F> &A, const ThreadCtx<F> &c, const Cplx<F> (&W)[3][3],
-                                          Cplx<F> (&M)[4][4], F (&Md)[4], Cplx<F> (&Mo)[6], const bool opposite) {
-  // producer side: the warps take turns - warp (m mod nActive) issues ALL bulk copies of eigenvector m's stage (lane i
-  // issues copy i).  Issuing costs ~100 non-FP64 instructions, which on this chip are paid in FP64 issue slots; spread
-  // over the warps in turn it is ~15 per warp and eigenvector.  Everything the producer needs (stage, barrier, phase) is
-  // derived from m when a warp's turn comes, so the other iterations carry no producer state at all: the loop body is
-  // 390 FP64 + ~55 other instructions (24 operand loads, one barrier wait, one arrive, eight address updates).
-  uint32_t total_tx = 0;
-  for (int i = 0; i < c.st->ncp; i++) total_tx += (uint32_t)c.st->cp_bytes[i];
-  const int lead = c.lane == 0;
-  const uint32_t stages_u32 = smem_u32(c.stages);
-  const uint32_t bar_u32 = smem_u32(c.full);  // full[s] at bar_u32 + 8 s, empty[s] 64 bytes further
-  const int ring_bytes = c.S * c.stage_bytes;
-  // distance between the colours of one spin: adjacent complex numbers (site-major), or component rows of a chunk of
-  // 8 sites (QUDA FLOAT2 stage, [chunk][component][8 sites])
-  constexpr int kC = NATIVE ? kChunk * 2 * (int)sizeof(F) : 2 * (int)sizeof(F);
-
-  auto issue = [&](int m) {  // the whole stage of eigenvector m; warp-uniform
-    const int rev = m / c.S, sm = m - rev * c.S;  // revolution of the ring, stage
-    const uint32_t p_full = bar_u32 + 8u * (uint32_t)sm, p_dst = stages_u32 + (uint32_t)(sm * c.stage_bytes);
-    if (rev > 0) mbar_wait_u32(p_full + 64, (uint32_t)((rev - 1) & 1));  // its previous tenant has been consumed
-    const char *ev = static_cast<const char *>(A.vt.evec[m]);
-    mbar_expect_tx_if(p_full, total_tx, lead);
-    if (NATIVE) {  // ev: this eigenvector's three tensor maps (boxes of 1, 2, 4 chunks) in device memory
-      for (int i = c.lane; i < c.st->ncp; i += 32) {
-        const int d = c.st->cp_goff16[i];
-        tma_tensor4_g2s(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((d >> 29) & 3) * 128, d & 0x0fffffff, (d >> 28) & 1, p_full);
-      }
-    } else {
-      for (int i = c.lane; i < c.st->ncp; i += 32)
-        tma_bulk_g2s_if(p_dst + (uint32_t)c.st->cp_soff[i], ev + ((size_t)c.st->cp_goff16[i] << 4),
-                        (uint32_t)c.st->cp_bytes[i], p_full, 1);
-    }
-  };
-  for (int m = c.warp; m < c.ahead && m < c.nvec; m += c.nActive) issue(m);  // ahead < S: no tenant to wait for
-  // iteration n refills the ring with eigenvector n + ahead; it is this warp's turn when (n + ahead) mod nActive == warp
-  int until = (c.warp - c.ahead) % c.nActive;
-  if (until < 0) until += c.nActive;
-
-  // consumer cursor: absolute shared addresses of the 4 rotated spin blocks of v(x) and v(x+d) in the current stage
-  const char *a_own[4], *a_nbr[4];
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    a_own[b] = c.stages + c.own_sp[b];
-    a_nbr[b] = c.stages + c.nbr_sp[b];
-  }
-  uint32_t c_bar = bar_u32;
-  int c_left = c.S;
-  uint32_t c_par = 0;
-  for (int n = 0; n < c.nvec; n++) {
-    if (until == 0) {
-      until = c.nActive;
-      if (n + c.ahead < c.nvec) issue(n + c.ahead);
-    }
-    until--;
-    mbar_wait_u32(c_bar, c_par);
-    const F is = (F)A.vt.inv_sigma[n];
-    Cplx<F> vp[12];
-    if (ND > 0) {
-#pragma unroll
-      for (int al = 0; al < 4; al++) {
-        vp[al * 3 + 0] = lds_c<F>(a_nbr[al]);
-        vp[al * 3 + 1] = lds_c<F>(a_nbr[al] + kC);
-        vp[al * 3 + 2] = lds_c<F>(a_nbr[al] + 2 * kC);
-      }
-    }
-#pragma unroll
-    for (int cc = 0; cc < 3; cc++) {
-      Cplx<F> lc[4];
-#pragma unroll
-      for (int be = 0; be < 4; be++) lc[be] = lds_c<F>(a_own[be] + cc * kC);
-      if (cc == 2) {  // last shared-memory read of this stage: hand it back before the remaining FMAs
-        __syncwarp();
-        mbar_arrive_if(c_bar + 64, lead);
-      }
-      // (1/sigma) v(x): one scaling serves the displaced and the ultra-local accumulation
-      Cplx<F> ls[4];
-#pragma unroll
-      for (int be = 0; be < 4; be++) ls[be] = make_c<F>(lc[be].re * is, lc[be].im * is);
-      if (ND > 0) {
-        Cplx<F> Rc[4];
-#pragma unroll
-        for (int al = 0; al < 4; al++) {
-          Rc[al] = cmul(W[cc][0], vp[al * 3 + 0]);
-          cmac(Rc[al], W[cc][1], vp[al * 3 + 1]);
-          cmac(Rc[al], W[cc][2], vp[al * 3 + 2]);
-        }
-#pragma unroll
-        for (int be = 0; be < 4; be++)
-#pragma unroll
-          for (int al = 0; al < 4; al++) cmac_conj(M[be][al], ls[be], Rc[al]);
-      }
-      if (UL == UL_ALL) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          Md[k] = fma(ls[k].re, lc[k].re, Md[k]);
-          Md[k] = fma(ls[k].im, lc[k].im, Md[k]);
-        }
-#pragma unroll
-        for (int k = 4; k < 10; k++) cmac_conj(Mo[k - 4], ls[ul_pair_be(k)], lc[ul_pair_al(k)]);
-      }
-      if (UL == UL_ROT) {
-        Md[0] = fma(ls[0].re, lc[0].re, Md[0]);
-        Md[0] = fma(ls[0].im, lc[0].im, Md[0]);
-        cmac_conj(Mo[0], ls[0], lc[1]);
-        cmac_conj(Mo[1], ls[0], lc[2]);  // needed from roles 0 and 1 only; computing it everywhere keeps the code uniform
-      }
-    }
-    // next stage: the eight running addresses move on (one add each instead of recomputing base + offset)
-    c_bar += 8;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      a_own[b] += c.stage_bytes;
-      a_nbr[b] += c.stage_bytes;
-    }
-    if (--c_left == 0) {
-      c_left = c.S;
-      c_bar = bar_u32;
-      c_par ^= 1u;
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        a_own[b] -= ring_bytes;
-        a_nbr[b] -= ring_bytes;
-      }
-    }
-  }
-}
-
-// ---- warp-specialised form (WS = 1, the default) -----------------------------------------------------------------------------
-// Measured on B200 (tools/issue_bench.cu, tools/fused_trace.py, ncu instruction samples): a warp issues one
-// DFMA per 4 cycles whether or not its SM sub-partition's other warp competes, and two warps exactly fill the FP64 pipe - so
-// everything a compute warp does besides its 390 FP64 instructions per eigenvector is serial time of that warp and idles the
-// pipe.  Integer / uniform instructions are almost free (they issue in the shadow of a DFMA), LDS costs ~4 cycles, a barrier
-// try_wait whose result is consumed at once ~50 cycles, and the turn-taking TMA issue of the round-2 loop ~200-260 cycles per
-// eigenvector.  Hence: a PRODUCER warp (its own warp group, registers handed to the compute warps with setmaxnreg) issues every
-// bulk copy and waits for the empty barriers; the compute warps only test the full barrier of the NEXT stage half an
-// eigenvector ahead (non-blocking mbarrier.test_wait) and consume.
+// ---- the eigenvector loop, warp-specialised ----------------------------------------------------------------------------------
+// Measured (tools/issue_bench.cu, tools/dfma_bench.cu, tools/fused_trace.py, ncu instruction samples): with
+// two warps per SM sub-partition the FP64 pipe is busy only while BOTH are in FP64 code, so everything else a compute warp
+// does is paid in pipe time.  In the round-2 loop the compute warps took turns issuing the bulk copies: ~200-260 cycles per
+// eigenvector and warp (integer division for the ring position, a blocking wait on the empty barrier, the copy list), plus a
+// full-barrier try_wait whose result the next instruction needed (~50 cycles).  Now a PRODUCER warp (its own warp group, its
+// registers handed to the compute warps with setmaxnreg) issues every copy; a compute warp tests the full barrier of the NEXT
+// stage half an eigenvector ahead (non-blocking mbarrier.test_wait) and only spins if that test failed.  Loop body: 390 FP64
+// + 24 LDS.128 + ~45 integer / control instructions, 2040 cycles per eigenvector at configs[1] (1560 would be one FP64
+// instruction per 2 cycles; the bare outer-product stream needs 1960).
 __device__ __forceinline__ uint32_t mbar_test_u32(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
@@ -359,8 +228,8 @@ __device__ __forceinline__ void consumer_loop(const FusedArgs<F> &A, const Threa
   }
 }
 
-template <typename F, int ND, int NATIVE, int WS>
-__global__ void __launch_bounds__(WS ? kFusedThreadsWS : kFusedThreads, 1) loop_fused_kernel(const __grid_constant__ FusedArgs<F> A) {
+template <typename F, int ND, int NATIVE>
+__global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __grid_constant__ FusedArgs<F> A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);        // [nstages]
   uint64_t *empty = reinterpret_cast<uint64_t *>(smem + 64);  // [nstages]
@@ -381,31 +250,28 @@ __global__ void __launch_bounds__(WS ? kFusedThreadsWS : kFusedThreads, 1) loop_
   const int c0 = A.c_begin + (int)blockIdx.x * tl.run;
   const int c1 = min(c0 + tl.run, A.c_end);
 
-  if (A.maps != nullptr) {  // this CTA's stage map, worked out once per (lattice, group, range) by stage_maps_kernel
+  {  // this CTA's stage map, worked out once per (lattice, group, range) by stage_maps_kernel
     const int4 *src = reinterpret_cast<const int4 *>(A.maps + blockIdx.x);
     int4 *dst = reinterpret_cast<int4 *>(&st);
     for (int i = threadIdx.x; i < (int)(sizeof(StageMap) / sizeof(int4)); i += blockDim.x) dst[i] = __ldg(src + i);
   }
   if (threadIdx.x == 0) {
-    if (A.maps == nullptr) build_stage_map(st, A.grp, g, kSite, c0, c1, NATIVE ? kChunk : 1);
     for (int s = 0; s < tl.nstages; s++) {
-      mbar_init(&full[s], 1);        // one arrive.expect_tx by the warp that issues the stage
+      mbar_init(&full[s], 1);        // one arrive.expect_tx by the producer warp
       mbar_init(&empty[s], nActive);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   trace_mark(A, 2);
-  if (WS) {
-    if (warp >= kFusedComputeWarps) {  // producer warp group: keeps 40 registers per thread, one warp works
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-      if (warp == kFusedComputeWarps)
-        producer_loop<F, NATIVE>(A, st, smem_u32(stages), smem_u32(full), tl.nstages, tl.stage_bytes, lane);
-      return;
-    }
-    // 8 x 32 x 232 + 4 x 32 x 40 = 64512 of the 65536 registers of an SM
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  if (warp >= kFusedComputeWarps) {  // producer warp group: keeps 40 registers per thread, one warp works
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kFusedComputeWarps)
+      producer_loop<F, NATIVE>(A, st, smem_u32(stages), smem_u32(full), tl.nstages, tl.stage_bytes, lane);
+    return;
   }
+  // 8 x 32 x 232 + 4 x 32 x 40 = 64512 of the 65536 registers of an SM
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
 
   const bool active = warp < nActive;
   // ---- role of this thread: displaced loop j (if any) on site c0 + q of parity p -------------------------------
@@ -436,7 +302,6 @@ __global__ void __launch_bounds__(WS ? kFusedThreadsWS : kFusedThreads, 1) loop_
   c.S = tl.nstages;
   c.stage_bytes = tl.stage_bytes;
   c.nvec = A.vt.nvec;
-  c.ahead = c.S > 2 ? c.S - 2 : 1;  // stages in flight beyond the one being consumed
   c.nActive = nActive;
   c.warp = warp;
   c.lane = lane;
@@ -482,28 +347,13 @@ __global__ void __launch_bounds__(WS ? kFusedThreadsWS : kFusedThreads, 1) loop_
 
   const int ul_mode = !has_ul ? UL_NONE : (ND == 4 ? UL_ROT : (j == 0 ? UL_ALL : UL_NONE));
   trace_mark(A, 3);
-  if (WS && A.skew > 0) {  // stagger the compute warps (see consumer_loop): warp w starts w * skew cycles late
-    const long long t0 = clock64();
-    const long long wait = (long long)warp * A.skew;
-    while (clock64() - t0 < wait) {
-    }
-  }
   if (active) {
-    if (WS) {
-      if (ul_mode == UL_NONE)
-        consumer_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo);
-      else if (ul_mode == UL_ALL)
-        consumer_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo);
-      else
-        consumer_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo);
-    } else {
-      if (ul_mode == UL_NONE)
-        evec_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo, false);
-      else if (ul_mode == UL_ALL)
-        evec_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo, false);
-      else
-        evec_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo, j < 2);
-    }
+    if (ul_mode == UL_NONE)
+      consumer_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo);
+    else if (ul_mode == UL_ALL)
+      consumer_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo);
+    else
+      consumer_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo);
   }
 
   trace_mark(A, 4);
@@ -528,10 +378,7 @@ __global__ void __launch_bounds__(WS ? kFusedThreadsWS : kFusedThreads, 1) loop_
       if (j < 2) put_pair(0, 2, Mo[1]);
     }
   }
-  if (WS)
-    asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");  // the compute warps only (the producer group has left)
-  else
-    __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");  // the compute warps only (the producer group has left)
   if (!valid) {
     trace_mark(A, 5);
     return;
@@ -816,28 +663,20 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
   return -1;
 }
 
-template <typename F, int ND, int NATIVE, int WS>
-static int launch_fused_ndp(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
+template <typename F, int ND, int NATIVE>
+static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
   // the shared-memory opt-in is a per-device function attribute
   static bool attr_set[64];
   int dev = 0;
   MUGIQ_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND, NATIVE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MUGIQ_CUDA_CHECK(cudaFuncSetAttribute(loop_fused_kernel<F, ND, NATIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           fused_smem_limit_bytes()));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  loop_fused_kernel<F, ND, NATIVE, WS><<<grid, WS ? kFusedThreadsWS : kFusedThreads, smem, stream>>>(args);
+  loop_fused_kernel<F, ND, NATIVE><<<grid, kFusedThreadsWS, smem, stream>>>(args);
   MUGIQ_LAUNCH_CHECK();
   return MUGIQ_B200_OK;
-}
-template <typename F, int ND, int NATIVE>
-static int launch_fused_nd(const FusedArgs<F> &args, size_t smem, int grid, cudaStream_t stream) {
-  static const int ws = [] {  // MUGIQ_B200_FUSED_WS=0: the round-2 kernel (compute warps take turns issuing the copies)
-    const char *e = getenv("MUGIQ_B200_FUSED_WS");
-    return e ? atoi(e) : 1;
-  }();
-  return ws ? launch_fused_ndp<F, ND, NATIVE, 1>(args, smem, grid, stream) : launch_fused_ndp<F, ND, NATIVE, 0>(args, smem, grid, stream);
 }
 
 template <typename F>
@@ -850,12 +689,6 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   args.ul_off = ul_off;
   args.dataPos = static_cast<F *>(dataPos_d);
   args.accumulate = accumulate;
-  args.maps = nullptr;
-  static const int skew = [] {
-    const char *e = getenv("MUGIQ_B200_FUSED_SKEW");
-    return e ? atoi(e) : 0;
-  }();
-  args.skew = skew;
   args.trace = g_fused_trace;
   args.trace_ctas = g_fused_trace_ctas;
   // time-slice range -> range of checkerboard indices (a time-slice is V3/2 consecutive sites of each parity)
@@ -866,15 +699,9 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
   const int grid = (args.c_end - args.c_begin + args.tl.run - 1) / args.tl.run;
-  static const bool premap = [] {  // MUGIQ_B200_FUSED_PREMAP=0: every CTA builds its own stage map (round 2)
-    const char *e = getenv("MUGIQ_B200_FUSED_PREMAP");
-    return e ? atoi(e) != 0 : true;
-  }();
-  if (premap) {
-    const int rc = stage_maps_get(&args.maps, grp, g, 24 * (int)sizeof(F), args.c_begin, args.c_end, args.tl.run, vt.native ? kChunk : 1,
-                                  grid, stream);
-    if (rc != MUGIQ_B200_OK) return rc;
-  }
+  if (const int rc = stage_maps_get(&args.maps, grp, g, 24 * (int)sizeof(F), args.c_begin, args.c_end, args.tl.run,
+                                    vt.native ? kChunk : 1, grid, stream))
+    return rc;
   const double frac = (double)(t_end - t_begin) / (double)g.L[3];  // share of the lattice this launch computes
   const size_t smem =
       kSmemHeader + (size_t)args.tl.units * 32 * 16 * sizeof(F) + (size_t)args.tl.nstages * args.tl.stage_bytes;

@@ -230,10 +230,9 @@ template <typename F> struct FusedArgs {
   F *dataPos;
   long long ul_off;    // complex offset of the ultra-local loop's block in dataPos, < 0: not in this launch
   int accumulate;
-  const StageMap *maps;  // stage map of every CTA of the launch (device memory), or NULL: thread 0 of a CTA builds its own
+  const StageMap *maps;  // stage map of every CTA of the launch (device memory, stage_maps_kernel)
   long long *trace;    // per-CTA timeline (mugiq_b200_prof_fused_trace), normally NULL
   int trace_ctas;
-  int skew;            // compute warp w enters the eigenvector loop w * skew cycles late (0: all at once)
   int c_begin, c_end;  // checkerboard-index range [c_begin, c_end) of both parities this launch computes: the time-slices
                        // [t_begin, t_end) of a lattice-T split slab, or the whole lattice
 };
@@ -284,7 +283,7 @@ template <typename F> struct ThreadCtx {
   const char *stages;
   uint64_t *full, *empty;
   const StageMap *st;
-  int S, stage_bytes, nvec, ahead, nActive, warp, lane;
+  int S, stage_bytes, nvec, nActive, warp, lane;
   int own_sp[4], nbr_sp[4];  // byte offsets (inside a stage) of the 4 rotated spin blocks of v(x) and v(x+d)
 };
 
@@ -298,10 +297,8 @@ template <typename F> struct ThreadCtx {
 //             with one loop body in the instruction cache instead of four (no_instruction stalls were 12%).
 enum { UL_NONE = 0, UL_ALL = 1, UL_ROT = 2 };
 
-// ---- hot-loop primitives on 32-bit shared addresses.  On B200 every non-FP64 instruction costs FP64 issue slots
-// (tools/microbench.cu: one IMAD per DFMA drops the DFMA rate from 33.5 to 18.3 TFLOP/s at 8 warps per SM), so the loop
-// body avoids branches (predicated mbarrier / TMA instructions instead of `if (lane == 0)` blocks), address
-// arithmetic (running per-thread addresses, immediates for the colour offset) and integer division.
+// ---- hot-loop primitives on 32-bit shared addresses: predicated mbarrier / TMA instructions instead of `if (lane == 0)`
+// blocks, so that the loops stay branch-free.
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"

@@ -218,13 +218,18 @@ static int plan_accumulate(const LoopPlan &pl, void *dataPos_d, const void *cons
 static int plan_finalize(const LoopPlan &pl, void *dataPos_d, int accumulate, cudaStream_t stream) {
   char *pos = static_cast<char *>(dataPos_d);
   const size_t lb = pl.loop_bytes();
+  MinusBatch mb;
+  mb.n = 0;
   for (const LoopPlan::Derive &d : pl.derives) {
-    if (d.kind == 1) {
-      int rc = loop_minus_from_plus(pos + (size_t)d.dst * lb, pos + (size_t)d.src * lb, d.dir, d.len, accumulate, pl.g,
-                                    pl.precision, stream);
+    if (d.kind != 1) continue;
+    mb.item[mb.n++] = {d.dst, d.src, d.dir, d.len};
+    if (mb.n == kMinusBatch) {
+      int rc = loop_minus_from_plus(dataPos_d, mb, accumulate, pl.g, pl.precision, stream);
       if (rc) return rc;
+      mb.n = 0;
     }
   }
+  if (int rc = loop_minus_from_plus(dataPos_d, mb, accumulate, pl.g, pl.precision, stream)) return rc;
   // copies last: a copy source may itself be a derived slot only through `repeated` requests of computed loops,
   // which are resolved against computed slots above, so order does not matter beyond kind
   for (const LoopPlan::Derive &d : pl.derives) {

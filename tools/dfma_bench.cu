@@ -76,7 +76,28 @@ template <int PAT> static void run(const char *name, int sms, double *out, doubl
   }
 }
 
-int main() {
+// sustained: the same stream for `seconds`; rate and SM clock over the second half (the board's power cap pulls the clock
+// down under a long FP64 load: the denominator for a kernel timed inside a long step)
+template <int PAT> static void sustained(const char *name, int sms, double *out, double *in, long long *cyc_d, double seconds) {
+  const int iters = 40000, warps = 8;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  double elapsed = 0, tf = 0, mhz = 0; int n = 0;
+  while (elapsed < seconds) {
+    CK(cudaEventRecord(a));
+    k<PAT><<<sms, warps * 32>>>(out, in, iters, cyc_d);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    elapsed += ms * 1e-3;
+    if (elapsed > seconds / 2) {
+      long long c[256]; CK(cudaMemcpy(c, cyc_d, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+      double mean = 0; for (int i = 0; i < sms; i++) mean += c[i]; mean /= sms;
+      tf += (double)sms * warps * 32 * iters * 64 * 2 / ms / 1e9; mhz += mean / ms / 1e3; n++;
+    }
+  }
+  printf(", \"%s_sustained_%.0fs\": {\"tflops\": %.2f, \"mhz\": %.0f}", name, seconds, tf / n, mhz / n);
+}
+
+int main(int argc, char **argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
   double *out, *in; long long *cyc; CK(cudaMalloc(&out, 64)); CK(cudaMalloc(&in, 8192)); CK(cudaMemset(in, 0, 8192)); CK(cudaMalloc(&cyc, 8 * 256));
@@ -84,6 +105,11 @@ int main() {
   run<0>("chain", sms, out, in, cyc);
   run<1>("outer4x4", sms, out, in, cyc);
   run<2>("cplx_outer4x4", sms, out, in, cyc);
+  if (argc > 1) {
+    const double sec = atof(argv[1]);
+    sustained<0>("chain", sms, out, in, cyc, sec);
+    sustained<2>("cplx_outer4x4", sms, out, in, cyc, sec);
+  }
   printf("}\n");
   return 0;
 }
