@@ -757,12 +757,18 @@ def run_ours(args, wl, name):
         ev_h = torch.empty((nev, V4, 12), dtype=torch.complex128, pin_memory=True)
         ev_h.copy_(ev_d)
         del loop
-        loop_h = Loop_Mugiq(prm, Eigsolve(list(ev_h), sig, L), device=dev, group=group, evec_batch=args.evec_batch,
+        # the links too live in PINNED host memory (numpy views of one pinned tensor): from pageable memory their 75 MB cost
+        # 5 ms of staged copy per step (profiles/r3_pcie_big.json: the eigenvector + dataPos copies alone need 97.7 ms)
+        prm_h = prm
+        if U is not None:
+            U_pin = torch.from_numpy(np.ascontiguousarray(U)).pin_memory()
+            prm_h, _ = make_params(wl, U_pin.numpy())
+        loop_h = Loop_Mugiq(prm_h, Eigsolve(list(ev_h), sig, L), device=dev, group=group, evec_batch=args.evec_batch,
                             copy_pos_to_host=True, stream_batch=args.stream_batch)
 
         def step_host():
             loop_h.MomProjDone = False
-            loop_h.displace.upload_gauge(prm) if loop_h.displace is not None else None   # H2D of the gauge field
+            loop_h.displace.upload_gauge(prm_h) if loop_h.displace is not None else None   # H2D of the gauge field
             loop_h.computeCoarseLoop()                                                    # H2D evecs, D2H dataPos + dataMom
 
         e2e_steps = max(1, min(args.steps, 5))

@@ -185,7 +185,7 @@ static int run_bench(std::map<std::string, std::string> &opt, const int X[4], Mu
   prm.Nmom = (int)prm.momMatrix.size();
   prm.doMomProj = MUGIQ_BOOL_TRUE;
   prm.FTSign = LOOP_FT_SIGN_MINUS;
-  // synthetic inputs: eigenvectors in pinned host memory (unit norm), links in pageable host memory
+  // synthetic inputs: eigenvectors (unit norm) and links in pinned host memory
   char *ev_h = nullptr;
   HOST_CUDA(cudaMallocHost((void **)&ev_h, fieldBytes * nEv));
   std::vector<double> sigma(nEv);
@@ -209,18 +209,19 @@ static int run_bench(std::map<std::string, std::string> &opt, const int X[4], Mu
       sumInvSigma += 1.0 / sigma[n];
     }
   }
-  std::vector<Float> gauge;
+  Float *gauge = nullptr;  // pinned as well: a staged copy from pageable memory costs 5 ms per step
+  const size_t gaugeLen = 4 * V4 * 18;
   QudaGaugeParam gp;
   if (prm.doNonLocal) {
-    gauge.resize(4 * V4 * 18);
+    HOST_CUDA(cudaMallocHost((void **)&gauge, gaugeLen * sizeof(Float)));
     uint64_t s = 12345;
-    for (Float &x : gauge) {
+    for (size_t k = 0; k < gaugeLen; k++) {
       s = s * 6364136223846793005ULL + 1442695040888963407ULL;
-      x = (double)((s >> 11) & ((1ULL << 53) - 1)) / (double)(1ULL << 53) - 0.5;
+      gauge[k] = (double)((s >> 11) & ((1ULL << 53) - 1)) / (double)(1ULL << 53) - 0.5;
     }
     for (int i = 0; i < 4; i++) {
       gp.X[i] = X[i];
-      prm.gauge[i] = gauge.data() + (size_t)i * V4 * 18;
+      prm.gauge[i] = gauge + (size_t)i * V4 * 18;
     }
     gp.cpu_prec = gp.cuda_prec = QUDA_DOUBLE_PRECISION;
     gp.gauge_order = QUDA_QDP_GAUGE_ORDER;
@@ -258,7 +259,7 @@ static int run_bench(std::map<std::string, std::string> &opt, const int X[4], Mu
   std::complex<double> tr = 0;
   for (size_t x = 0; x < V4; x++) tr += loop.hostDataPos()[x];
   const double chk = std::abs(tr - sumInvSigma) / sumInvSigma;
-  const double h2d = (double)fieldBytes * nEv + (prm.doNonLocal ? (double)gauge.size() * sizeof(Float) : 0.0);
+  const double h2d = (double)fieldBytes * nEv + (prm.doNonLocal ? (double)gaugeLen * sizeof(Float) : 0.0);
   const double d2h = (double)(loop.numElemPos() + loop.numElemMom()) * 2 * sizeof(Float);
   const double units = (double)nEv * V4 * loop.nLoop();
   printf("{\"value\": %.6e, \"unit\": \"eigvec*site*loop contractions/s (16 gamma each)\", \"ms_per_step\": %.4f, \"steps\": %d, "
