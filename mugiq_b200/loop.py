@@ -314,7 +314,13 @@ class Loop_Mugiq:
         the fused kernel runs on the extended slab."""
         es, ts = self.eigsolve, self.tsplit
         nb = max(1, min(self.stream_batch, es.nEv))
+        # the halo of the first batch is the only one nothing hides (0.29 ms for 200 slabs of 16^3x32): start with an eighth
+        # of a batch, whose halo lands ~8x sooner, and push the rest under its kernels
+        # (the first regular batch is split in two, so every later batch starts where it did before)
         batches = [(b0, min(es.nEv, b0 + nb)) for b0 in range(0, es.nEv, nb)]
+        first = max(8, nb // 8)
+        if batches[0][1] - batches[0][0] > 2 * first:
+            batches = [(0, first), (first, batches[0][1])] + batches[1:]
         # only the interior is computed; the halos are read.  Plus-t loops read eigenvector slices above the interior,
         # minus-t loops that are computed directly read below it; minus-t loops DERIVED from their plus partner need the
         # partner's loop values below the interior instead, fetched once after the eigenvector sum.
