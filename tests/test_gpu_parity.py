@@ -267,6 +267,52 @@ def test_loop_plan_batches(ops, oracle, L, name, symmetric, monkeypatch):
     plan.close()
 
 
+def test_loop_plan_many_derived_loops(ops, oracle):
+    """More minus loops derived from their plus partners than one finalize launch takes (kMinusBatch = 32): 36 + 3 pairs."""
+    L = (4, 4, 8, 40)
+    nEv = 2
+    ev = synth.random_evecs_np(L, nEv, seed=43)
+    sig = synth.sigmas(nEv)
+    U = synth.random_gauge(L, seed=43)
+    entries = [(3, 1, 1, 36), (3, 0, 1, 36), (2, 1, 1, 3), (2, 0, 1, 3)]
+    ref = oracle.compute_loop(ev, sig, U, entries, L)
+    gd = ops.gauge_upload(U, L)
+    plan = ops.LoopPlan(gd, entries, L)
+    assert plan.info()["derived"] == 39
+    out = torch.full(ref.shape, 1.0 + 1.0j, dtype=torch.complex128, device="cuda")
+    plan.accumulate(out, [dev(ev[i]) for i in range(nEv)], sig, accumulate=False)
+    plan.finalize(out)
+    assert rel_err(host(out), ref) < TOL_F64
+    plan.close()
+
+
+def test_fused_trace_timeline(ops):
+    """mugiq_b200_prof_fused_trace: every CTA of a fused launch stamps its SM and five ordered times; NULL switches it off."""
+    L = (8, 8, 8, 8)
+    nEv = 6
+    ev = dev(synth.random_evecs_np(L, nEv, seed=44))
+    sig = synth.sigmas(nEv)
+    gd = ops.gauge_upload(synth.random_gauge(L, seed=44), L)
+    plan = ops.LoopPlan(gd, [(0, 1, 1, 1), (1, 1, 1, 1), (2, 1, 1, 1), (3, 1, 1, 1)], L)
+    out = torch.zeros((plan.nLoop, 16, ev.shape[1]), dtype=torch.complex128, device="cuda")
+    ncta = 8 * 8 * 8 * 8 // 2 // 32
+    buf = torch.zeros(16 * (ncta + 4), dtype=torch.int64, device="cuda")
+    ops.prof_fused_trace(buf)
+    plan.accumulate(out, list(ev), sig, accumulate=False)
+    torch.cuda.synchronize()
+    ops.prof_fused_trace(None)
+    t = buf.cpu().numpy().reshape(-1, 16)
+    assert (t[:ncta, 1] > 0).all() and (t[ncta:] == 0).all()
+    assert (t[:ncta, 0] >= 0).all() and (t[:ncta, 0] < 256).all()
+    for k in range(1, 5):
+        assert (t[:ncta, k + 1] >= t[:ncta, k]).all() and (t[:ncta, 9 + k] > t[:ncta, 8 + k]).all()
+    buf.zero_()
+    plan.accumulate(out, list(ev), sig, accumulate=False)
+    torch.cuda.synchronize()
+    assert int(buf.abs().sum().item()) == 0
+    plan.close()
+
+
 def test_loop_plan_many_vectors(ops, oracle):
     """More eigenvectors than one launch's pointer table (kFusedMaxVec = 256): chunked launches accumulate."""
     L = (4, 2, 2, 2)
