@@ -858,7 +858,7 @@ def run_ours(args, wl, name):
         except Exception as exc:
             config4 = {"error": repr(exc)[:300]}
             torch.cuda.empty_cache()
-        if world > 1:
+        if world > 1 and not args.no_tsplit_extra:
             try:
                 tsplit_obj = leg_tsplit(h, max(2, min(args.steps, 4)), 2)
             except Exception as exc:
@@ -945,6 +945,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config4 / tsplit objects")
+    ap.add_argument("--no-tsplit-extra", action="store_true", help="skip the `tsplit` object (keep `config4`)")
     ap.add_argument("--no-tsplit-full", action="store_true", help="skip the 2000-eigenvector pass of the `tsplit` object")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

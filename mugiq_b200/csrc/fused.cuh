@@ -58,7 +58,7 @@ void fused_set_trace(long long *trace_d, long long capacity_ctas);
 
 // host-only self-check of the tiling of one launch group (fused_kernel.cu); out = {run, units, nstages, stage_bytes,
 // max copies per stage, mean sites staged per CTA, sites not found in their stage, malformed stage maps}
-int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, int native,
+int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, int native, bool with_ul,
                        long long out[8]);
 // device addresses of the tensor maps (three per eigenvector: boxes of 1, 2, 4 chunks of 8 sites) of QUDA FLOAT2 fields,
 // encoded on first use and cached per (address, lattice, precision); new entries are uploaded on `stream`

@@ -242,7 +242,12 @@ __global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __
   trace_mark(A, 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_ul = A.ul_off >= 0;
-  constexpr int nrole = ND > 0 ? ND : 1;  // a launch without displaced loops runs one pure ultra-local role
+  // roles = threads working on one site: one per displaced loop; the ultra-local matrix rides with them when there are four
+  // (UL_ROT: shared out, same code in every warp), is the only role when there are none, and otherwise gets a role of its
+  // own - a warp that only reads v(x) - instead of loading role 0 with all ten entries (474 against 354 FP64 instructions
+  // per eigenvector and more registers than the compute warps have)
+  const bool ul_role = has_ul && ND >= 1 && ND <= 3;
+  const int nrole = (ND > 0 ? ND : 1) + (ul_role ? 1 : 0);
   const int nActive = nrole * tl.units;   // compute warps in use
   constexpr int kSite = 24 * (int)sizeof(F);
 
@@ -284,6 +289,7 @@ __global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __
   const int cb = c0 + q;
   const size_t x_eo = (size_t)p * g.volumeCB + (size_t)cb;
   const bool ul_rot = has_ul && ND == 4;  // see UL_ROT
+  const bool ul_thread = ul_role && j == ND;  // this warp accumulates the ultra-local matrix and nothing else
   const int s_own = max(stage_site(st, p, cb), 0);
   // Spin-label rotation against bank conflicts: the 8 lanes of a quarter-warp read 16 B each at a 192-byte site stride,
   // i.e. bank group (12 s + 3 k + c) mod 8 for stage position s and rotation k; with k = (lane / 2) mod 4 the groups are
@@ -311,8 +317,8 @@ __global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __
 #pragma unroll
     for (int b = 0; b < 4; b++) c.own_sp[b] = off + ((b + k_own) & 3) * kSpin;
   }
-  const FusedLoop lp = A.grp.loop[ND > 0 ? j : 0];
-  if (ND > 0) {
+  const FusedLoop lp = A.grp.loop[ND > 0 ? min(j, ND - 1) : 0];
+  if (ND > 0 && !ul_thread) {
     // neighbour x + sign*len*dir and its place in the stage
     const int s_nbr = max(stage_site(st, (p + lp.len) & 1, neighbour_cb(g, lp, p, cb)), 0);
     k_nbr = k_bank;
@@ -339,19 +345,19 @@ __global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __
   Cplx<F> W[3][3];
 #pragma unroll
   for (int k = 0; k < 9; k++) W[k / 3][k % 3] = make_c<F>(0, 0);
-  if (ND > 0 && active) {
+  if (ND > 0 && active && !ul_thread) {
     const F *pw = static_cast<const F *>(lp.W) + x_eo * (2 * kLinkLen);
 #pragma unroll
     for (int k = 0; k < 9; k++) W[k / 3][k % 3] = ldg_c<F>(pw + 2 * k);
   }
 
-  const int ul_mode = !has_ul ? UL_NONE : (ND == 4 ? UL_ROT : (j == 0 ? UL_ALL : UL_NONE));
+  const int ul_mode = !has_ul ? UL_NONE : (ND == 4 ? UL_ROT : ((ND == 0 || ul_thread) ? UL_ALL : UL_NONE));
   trace_mark(A, 3);
   if (active) {
     if (ul_mode == UL_NONE)
       consumer_loop<F, ND, UL_NONE, NATIVE>(A, c, W, M, Md, Mo);
     else if (ul_mode == UL_ALL)
-      consumer_loop<F, ND, UL_ALL, NATIVE>(A, c, W, M, Md, Mo);
+      consumer_loop<F, 0, UL_ALL, NATIVE>(A, c, W, M, Md, Mo);
     else
       consumer_loop<F, ND, UL_ROT, NATIVE>(A, c, W, M, Md, Mo);
   }
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __
     trace_mark(A, 5);
     return;
   }
-  if (ND > 0) {
+  if (ND > 0 && !ul_thread) {
     unrotate_rt<F, true>(M, k_own);
     unrotate_rt<F, false>(M, k_nbr);
     Cplx<F> T[16];
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kFusedThreadsWS, 1) loop_fused_kernel(const __
       st_c<F>(po, o);
     }
   }
-  if (has_ul && j == 0) {  // role 0 of every site gathers the Hermitian matrix and writes the ultra-local loop
+  if (has_ul && j == (ul_role ? ND : 0)) {  // one role of every site gathers the Hermitian matrix and writes the ultra-local loop
     const F *px = xch + (size_t)nid * 16;
     Cplx<F> M0[4][4];
 #pragma unroll
@@ -582,8 +588,9 @@ static bool fused_choose_tiling(FusedTiling &tl, const FusedGroup &grp, const La
 }
 
 static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom &g, int precision, int smem_limit, int c_begin,
-                          int c_end, int native = 0) {
-  const int nrole = grp.nloops > 0 ? grp.nloops : 1;
+                          int c_end, int native, bool with_ul) {
+  // roles of the kernel (loop_fused_kernel): the ultra-local matrix has its own role beside 1..3 displaced loops
+  const int nrole = (grp.nloops > 0 ? grp.nloops : 1) + ((with_ul && grp.nloops >= 1 && grp.nloops <= 3) ? 1 : 0);
   return fused_choose_tiling(tl, grp, g, precision, c_begin, c_end, kFusedComputeWarps, nrole, smem_limit - kSmemHeader,
                              32 * 16 * (int)prec_bytes(precision), 3, native ? kChunk : 1);
 }
@@ -591,13 +598,13 @@ static bool choose_tiling(FusedTiling &tl, const FusedGroup &grp, const LatGeom 
 // Host-only self-check of the tiling (no GPU needed; exported as mugiq_b200_fused_tiling_check for the CPU tests): for
 // every CTA of a launch, the stage map must be sorted, disjoint and within the sized stage, and every thread's own and
 // neighbour site must lie in it.
-int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, int native,
+int fused_tiling_check(const FusedGroup &grp, const LatGeom &g, int precision, int t_begin, int t_end, int native, bool with_ul,
                        long long out[8]) {
   FusedTiling tl;
   const int V3h = g.V3 / 2, c_begin = t_begin * V3h, c_end = t_end * V3h;
   if (native && g.volumeCB % kChunk)
     return set_error(MUGIQ_B200_EINVAL, "fused_tiling_check: QUDA-ordered eigenvectors need volumeCB to be a multiple of %d", kChunk);
-  if (!choose_tiling(tl, grp, g, precision, 227 * 1024, c_begin, c_end, native))
+  if (!choose_tiling(tl, grp, g, precision, 227 * 1024, c_begin, c_end, native, with_ul))
     return set_error(MUGIQ_B200_EINVAL, "fused_tiling_check: no tiling fits");
   const int site = 24 * (int)prec_bytes(precision);
   long long misses = 0, bad_maps = 0, stage_sites = 0, ctas = 0;
@@ -658,7 +665,7 @@ int fused_max_loops_per_group(const LatGeom &g, int precision) {
       grp.loop[j].out_off = 0;
     }
     FusedTiling tl;
-    if (choose_tiling(tl, grp, g, precision, fused_smem_limit_bytes(), 0, g.volumeCB)) return nl;
+    if (choose_tiling(tl, grp, g, precision, fused_smem_limit_bytes(), 0, g.volumeCB, 0, false)) return nl;
   }
   return -1;
 }
@@ -695,7 +702,7 @@ static int launch_fused(void *dataPos_d, const FusedGroup &grp, long long ul_off
   const int V3h = g.V3 / 2;
   args.c_begin = t_begin * V3h;
   args.c_end = t_end * V3h;
-  if (!choose_tiling(args.tl, grp, g, precision, fused_smem_limit_bytes(), args.c_begin, args.c_end, vt.native))
+  if (!choose_tiling(args.tl, grp, g, precision, fused_smem_limit_bytes(), args.c_begin, args.c_end, vt.native, ul_off >= 0))
     return set_error(MUGIQ_B200_EINVAL, "loop_fused: no tiling fits %d loops on a %dx%dx%dx%d lattice", grp.nloops, g.L[0],
                      g.L[1], g.L[2], g.L[3]);
   const int grid = (args.c_end - args.c_begin + args.tl.run - 1) / args.tl.run;

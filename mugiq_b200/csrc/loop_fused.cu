@@ -329,7 +329,8 @@ int mugiq_b200_fused_tiling_check(const mugiq_b200_disp_entry_t *entries, int ne
   if (group >= (int)pl.groups.size()) return set_error(MUGIQ_B200_EINVAL, "%s: the plan has %zu groups", who, pl.groups.size());
   if (t_end < 0) t_end = geom->L[3];
   if (t_begin < 0 || t_begin >= t_end || t_end > geom->L[3]) return set_error(MUGIQ_B200_EINVAL, "%s: bad time-slice range", who);
-  return fused_tiling_check(pl.groups[group], pl.g, pl.precision, t_begin, t_end, evec_order == MUGIQ_B200_ORDER_FLOAT2, out);
+  // the ultra-local loop rides in the first group (plan_accumulate_range)
+  return fused_tiling_check(pl.groups[group], pl.g, pl.precision, t_begin, t_end, evec_order == MUGIQ_B200_ORDER_FLOAT2, group == 0, out);
 }
 
 int mugiq_b200_loop_plan_destroy(mugiq_b200_loop_plan_t *plan) {
