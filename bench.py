@@ -326,9 +326,8 @@ class Harness:
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.args = torch, dist, args
-        self.rank = int(os.environ.get("RANK", "0"))
-        self.world = int(os.environ.get("WORLD_SIZE", "1"))
-        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        from mugiq_b200.dist import env_rank_world
+        self.rank, self.world, self.local_rank = env_rank_world()
         if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
         assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"

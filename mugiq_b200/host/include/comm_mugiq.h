@@ -10,7 +10,7 @@
 #define MUGIQ_B200_COMM_MUGIQ_H
 #include <cstddef>
 
-#include "mugiq_api.h"
+#include "mugiq.h"
 
 struct MugiqComm;  // opaque
 struct mugiq_b200_comm_s;

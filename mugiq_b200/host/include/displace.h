@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "eigsolve_mugiq.h"
-#include "mugiq_api.h"
+#include "mugiq.h"
 #include "mugiq_b200.h"
 
 using namespace quda;

@@ -6,7 +6,7 @@
 #define MUGIQ_B200_EIGSOLVE_MUGIQ_H
 #include <vector>
 
-#include "mugiq_api.h"
+#include "mugiq.h"
 
 struct MugiqEigParam {
   QudaEigParam *QudaEigParams;

@@ -6,7 +6,7 @@
 #define MUGIQ_B200_LOOP_MUGIQ_H
 #include "displace.h"
 #include "eigsolve_mugiq.h"
-#include "mugiq_api.h"
+#include "mugiq.h"
 
 using namespace quda;
 

@@ -2,7 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "mugiq_api.h"
+#include "mugiq.h"
 #include "mugiq_b200.h"
 
 // a non-zero status of the C-ABI is what the reference reports through errorQuda / checkCudaError()

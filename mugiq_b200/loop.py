@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .dist import allreduce_loop_buffer
 from ._lib import PREC_DOUBLE, PREC_SINGLE
 from .lattice import Lattice
 from .params import (MugiqLoopParam, LoopComputeParam, MugiqError, which_displace, DISPLACE_TYPE_COVARIANT,
@@ -265,8 +266,7 @@ class Loop_Mugiq:
                 if fused_reduce:
                     self.comm.allreduce_pos(self.dataPos_d, plan.computed_slots(), self.L)
             if reduce_pos and not fused_reduce:
-                import torch.distributed as dist
-                dist.all_reduce(torch.view_as_real(self.dataPos_d), op=dist.ReduceOp.SUM, group=self.group)
+                allreduce_loop_buffer(self.dataPos_d, group=self.group)
             # slots derived after the eigenvector sum (minus-direction partners, repeated entries): linear in the
             # computed slots, so they are filled after the cross-rank sum and need none of their own
             plan.finalize(self.dataPos_d)
@@ -441,8 +441,7 @@ class Loop_Mugiq:
             if self.comm is not None:
                 self.comm.allreduce(self.dataMom_d)
             else:
-                import torch.distributed as dist
-                dist.all_reduce(torch.view_as_real(self.dataMom_d), op=dist.ReduceOp.SUM, group=self.group)
+                allreduce_loop_buffer(self.dataMom_d, group=self.group)
         self.dataMom_h = self.dataMom_d.cpu()
         # single spatial block: MPI_Reduce over COMM_SPACE is the identity
         self.dataMom = self.dataMom_h
