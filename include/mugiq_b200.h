@@ -308,8 +308,9 @@ int mugiq_b200_momproj_pos(void *mom_d, const void *dataPos_d, const void *phase
  *                    of a position-space buffer - the "per-time-slice loop buffer" - as one grouped NCCL launch
  *   loop_plan_accumulate_allreduce : mugiq_b200_loop_plan_accumulate for the LAST (or only) eigenvector batch of a
  *                    sharded run, fused with the sum of every slot the plan computes: the lattice is processed in
- *                    `nchunks` time-slice chunks, and the all-reduce of chunk k runs on a high-priority side stream
- *                    while the kernels of chunk k+1 compute (only the last chunk's sum is exposed).  On return,
+ *                    time-slice chunks - each half of what is left, down to Lt / (2 nchunks) slices; nchunks <= 1: one -
+ *                    and the all-reduce of chunk k runs on a high-priority side stream while the kernels of chunk k+1
+ *                    compute (only the last, smallest chunk's sum is exposed).  On return,
  *                    work enqueued on `stream` sees the summed buffer; call loop_plan_finalize afterwards (the derived
  *                    slots are linear in the computed ones, so they need no sum of their own). */
 #define MUGIQ_B200_COMM_ID_BYTES 128
@@ -322,6 +323,15 @@ int mugiq_b200_allreduce(void *buf_d, long long count, int precision, mugiq_b200
 int mugiq_b200_allgather(void *recv_d, const void *send_d, long long bytes, mugiq_b200_comm_t *comm, void *stream);
 int mugiq_b200_allreduce_pos(void *dataPos_d, const int *slots_h, int nslots, int t_begin, int t_end,
                              const mugiq_b200_geom_t *geom, mugiq_b200_comm_t *comm, void *stream);
+/* Peer transport of the overlapped position-space sum: every rank maps all ranks' position-space buffers and one staging
+ * area per rank (mugiq_b200_peer_alloc / _open; own pointers at index `rank`) and attaches the tables.  While attached,
+ * loop_plan_accumulate_allreduce on the attached buffer moves the chunks with the copy engines (reduce-scatter into the
+ * owners' staging areas, a small summing kernel, all-gather into the peers' buffers; one-element NCCL all-reduces order
+ * the rounds) instead of NCCL's all-reduce kernels, which compete with the FP64-bound loop kernels for SMs.
+ *   comm_stage_bytes  : staging bytes per rank for the plan's computed loops summed in `nchunks` chunks over `size` ranks
+ *   comm_attach_peers : tables of `size` device pointers each (256-byte aligned); NULL, NULL detaches */
+long long mugiq_b200_comm_stage_bytes(const mugiq_b200_loop_plan_t *plan, int nchunks, int size);
+int mugiq_b200_comm_attach_peers(mugiq_b200_comm_t *comm, void *const *peer_pos_d, void *const *peer_stage_d, long long stage_bytes);
 int mugiq_b200_loop_plan_accumulate_allreduce(const mugiq_b200_loop_plan_t *plan, void *dataPos_d, const void *const *evec_d,
                                               const double *sigma_h, int nvec, int accumulate, mugiq_b200_comm_t *comm,
                                               int nchunks, void *stream);

@@ -78,6 +78,8 @@ SYMBOLS = {
     "mugiq_b200_loop_feed_finish": (_i, [_vp, C.POINTER(_ll)]),
     "mugiq_b200_comm_unique_id": (_i, [_vp]),
     "mugiq_b200_comm_create": (_i, [C.POINTER(_vp), _vp, _i, _i]),
+    "mugiq_b200_comm_stage_bytes": (_ll, [_vp, _i, _i]),
+    "mugiq_b200_comm_attach_peers": (_i, [_vp, _pvp, _pvp, _ll]),
     "mugiq_b200_comm_destroy": (_i, [_vp]),
     "mugiq_b200_comm_info": (_i, [_vp, _pi, _pi, _pi]),
     "mugiq_b200_allreduce": (_i, [_vp, _ll, _i, _vp, _vp]),

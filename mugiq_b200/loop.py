@@ -130,8 +130,12 @@ class Loop_Mugiq:
 
     def __init__(self, loopParams_: MugiqLoopParam, eigsolve_: Eigsolve, device=None, group=None, evec_batch=64,
                  stream_batch=16, copy_pos_to_host=True, fused_momproj=True, tsplit=None, comm=None, reduce_pos=None,
-                 allreduce_chunks=8):
+                 allreduce_chunks=8, peer_reduce=False):
         self.eigsolve = eigsolve_
+        # with `comm`: the overlapped position-space sum moves its chunks with the copy engines over peer-mapped buffers
+        # (mugiq_b200_comm_attach_peers) instead of NCCL's all-reduce kernels; needs `group` for the handle exchange
+        self.peer_reduce = bool(peer_reduce) and comm is not None and comm.size > 1
+        self._peer = None
         self.group = group
         # ops.Comm over the same ranks as `group`: the cross-rank sums then go through the library's own NCCL calls
         # (mugiq_b200_allreduce*), the position-space one overlapped with the kernels chunk by chunk; without it they
@@ -217,7 +221,12 @@ class Loop_Mugiq:
         self.nElemMomLoc = p.nG * p.Nmom * p.locT * p.nLoop
         self.nElemMomTot = p.nG * p.Nmom * p.totT * p.nLoop
         self.nElemPhMat = p.Nmom * p.locV3
-        self.dataPos_d = torch.zeros((p.nLoop, p.nG, p.locV4), dtype=self.dtype, device=self.device)
+        if self.peer_reduce:  # one IPC-shareable allocation the other ranks map
+            self._pos_buf = ops.PeerBuffer(p.nLoop * p.nG * p.locV4 * (16 if self.dtype == torch.complex128 else 8), device=self.device)
+            self.dataPos_d = self._pos_buf.tensor((p.nLoop, p.nG, p.locV4), self.dtype)
+            self.dataPos_d.zero_()
+        else:
+            self.dataPos_d = torch.zeros((p.nLoop, p.nG, p.locV4), dtype=self.dtype, device=self.device)
         self.dataPosExt_d = None
         if self.tsplit is not None:
             self.dataPosExt_d = torch.zeros((p.nLoop, p.nG, Lattice(self.L_run).volume), dtype=self.dtype, device=self.device)
@@ -257,6 +266,8 @@ class Loop_Mugiq:
                     b1 = min(es.nEv, b0 + self.evec_batch)
                     prep = self._prepared_batch(plan, b0, b1, es.eVecs[b0:b1])
                     if fused_reduce and b0 == starts[-1]:
+                        if self.peer_reduce and self._peer is None:
+                            self._attach_peer_reduce(plan)
                         plan.accumulate_allreduce(self.dataPos_d, prep, self.comm, accumulate=b0 > 0,
                                                   nchunks=self.allreduce_chunks)
                     else:
@@ -279,6 +290,43 @@ class Loop_Mugiq:
             if p.doMomProj:
                 self.performMomentumProjection()
         return self
+
+    def _attach_peer_reduce(self, plan):
+        """Peer transport of the overlapped sum: exchange the IPC handles of dataPos_d and of a staging area over the process
+        group, map every peer's pair, hand the tables to the communicator (once per Loop_Mugiq)."""
+        import torch.distributed as dist
+        comm = self.comm
+        nbytes = comm.stage_bytes(plan, self.allreduce_chunks)
+        stage = ops.PeerBuffer(nbytes, device=self.device)
+        mine = (self._pos_buf.handle, stage.handle)
+        every = [None] * comm.size
+        dist.all_gather_object(every, mine, group=self.group)
+        pos_ptrs, stage_ptrs, opened = [], [], []
+        for r, (hp, hs) in enumerate(every):
+            if r == comm.rank:
+                pos_ptrs.append(self._pos_buf.ptr)
+                stage_ptrs.append(stage.ptr)
+            else:
+                a, b = ops.peer_open(hp, self.device), ops.peer_open(hs, self.device)
+                opened += [a, b]
+                pos_ptrs.append(a)
+                stage_ptrs.append(b)
+        comm.attach_peers(pos_ptrs, stage_ptrs, nbytes)
+        self._peer = {"stage": stage, "opened": opened}
+
+    def close_peer_reduce(self):
+        """Collective: detach and unmap the peer transport (before the buffers are freed)."""
+        if self._peer is None:
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        self.comm.attach_peers(None, None, 0)
+        dist.barrier(group=self.group)
+        for ptr in self._peer["opened"]:
+            ops.peer_close(ptr, self.device)
+        dist.barrier(group=self.group)
+        self._peer["stage"].free()
+        self._peer = None
 
     def _prepared_batch(self, plan, b0, b1, vecs):
         """Argument tables (pointer array, sigma array) of the resident batch [b0, b1): built once and reused while the

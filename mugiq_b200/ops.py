@@ -468,6 +468,23 @@ class Comm:
                                                        C.byref(geom), self._h, _stream()))
         return dataPos
 
+    def stage_bytes(self, plan, nchunks):
+        """Staging bytes per rank of the peer transport for `plan` summed in `nchunks` chunks."""
+        n = _lib.load().mugiq_b200_comm_stage_bytes(plan._h, int(nchunks), self.size)
+        if n < 0:
+            check(int(n))
+        return int(n)
+
+    def attach_peers(self, peer_pos, peer_stage, stage_bytes):
+        """peer_pos / peer_stage: device addresses (ints) of every rank's position-space buffer / staging area as mapped in
+        this process, own allocation at index `rank`; None, None detaches."""
+        lib = _lib.load()
+        if peer_pos is None:
+            check(lib.mugiq_b200_comm_attach_peers(self._h, None, None, 0))
+            return
+        with torch.cuda.device(self.device):
+            check(lib.mugiq_b200_comm_attach_peers(self._h, ptr_array(list(peer_pos)), ptr_array(list(peer_stage)), int(stage_bytes)))
+
     def allgather(self, send):
         _dev(send)
         recv = torch.empty((self.size,) + tuple(send.shape), dtype=send.dtype, device=send.device)

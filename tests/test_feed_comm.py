@@ -196,14 +196,19 @@ comm = ops.Comm(dist.group.WORLD)
 out = {{}}
 for mode, kw in [("overlapped", dict(comm=comm, reduce_pos=True, allreduce_chunks=4)), ("after", dict(comm=comm, reduce_pos=True, allreduce_chunks=1)),
                  ("torch", dict(reduce_pos=True)), ("mom_only", dict(comm=comm, reduce_pos=False)),
-                 ("host_streamed", dict(comm=comm, reduce_pos=True, host=True))]:
+                 ("host_streamed", dict(comm=comm, reduce_pos=True, host=True)),
+                 ("peer_dma", dict(comm=comm, reduce_pos=True, allreduce_chunks=4, peer_reduce=True))]:
     host = kw.pop("host", False)
     vecs = [torch.from_numpy(ev[n]).pin_memory() if host else torch.from_numpy(ev[n]).cuda() for n in range(lo, hi)]
     loop = Loop_Mugiq(prm, Eigsolve(vecs, sig[lo:hi], L), device=torch.device("cuda", rank), group=dist.group.WORLD, evec_batch=2,
                       stream_batch=2, copy_pos_to_host=False, **kw)
     loop.computeCoarseLoop()
+    if mode == "peer_dma":  # a second step on the same mapped buffers (the staging halves alternate)
+        loop.MomProjDone = False
+        loop.computeCoarseLoop()
     out[mode + "_pos"] = loop.dataPos_d.cpu().numpy()
     out[mode + "_mom"] = loop.dataMom.numpy()
+    loop.close_peer_reduce()
 np.savez({out!r} + str(rank) + ".npz", **out)
 torch.cuda.synchronize()
 comm.close()
@@ -214,7 +219,8 @@ dist.destroy_process_group()
 @pytest.mark.gpu
 def test_eigenvector_shards_over_the_library_communicator(oracle, tmp_path):
     """Two ranks, one per GPU: every form of the cross-rank sum (chunked all-reduce overlapped with the kernels, one
-    all-reduce after them, torch.distributed, projected buffer only, host-streamed eigenvectors) against the oracle."""
+    all-reduce after them, torch.distributed, projected buffer only, host-streamed eigenvectors, chunks moved by the copy
+    engines over peer-mapped buffers) against the oracle."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (NCCL does not put two ranks on one device)")
     from oracle import numpy_check as npc
@@ -241,7 +247,7 @@ def test_eigenvector_shards_over_the_library_communicator(oracle, tmp_path):
     ref_mom = npc.momentum_projection(ref, momenta_up_to(1), -1, Lx)
     for rank in range(2):
         z = np.load(tmp_path / f"rank{rank}.npz")
-        for mode in ("overlapped", "after", "torch", "host_streamed"):
+        for mode in ("overlapped", "after", "torch", "host_streamed", "peer_dma"):
             assert rel_err(z[mode + "_pos"], ref) < TOL_F64, (rank, mode)
             assert rel_err(z[mode + "_mom"], ref_mom) < TOL_F64, (rank, mode)
         assert rel_err(z["mom_only_mom"], ref_mom) < TOL_F64
