@@ -591,7 +591,13 @@ def leg_config4(h, steps, warmup):
                      ("pos_allreduce_peer_dma", dict(reduce_pos=True, comm=h.library_comm(), allreduce_chunks=h.args.allreduce_chunks,
                                                      peer_reduce=True))]
     for label, kw in variants:
-        loop = Loop_Mugiq(prm, es, device=h.dev, group=h.group, evec_batch=256, copy_pos_to_host=False, **kw)
+        try:
+            loop = Loop_Mugiq(prm, es, device=h.dev, group=h.group, evec_batch=256, copy_pos_to_host=False, **kw)
+            loop.MomProjDone = False
+            loop.computeCoarseLoop()   # first step outside the timed region (plan, peer mapping)
+        except Exception as exc:       # a transport this box cannot do (no IPC between the devices) must not cost the other forms
+            out[label] = {"error": repr(exc)[:300]}
+            continue
 
         def step():
             loop.MomProjDone = False
@@ -620,11 +626,13 @@ def leg_config4(h, steps, warmup):
         out[label] = o
         loop.close_peer_reduce()
         del loop
-    best = out.get("pos_allreduce_overlapped", out["without_pos_allreduce"])
-    if "pos_allreduce_peer_dma" in out and out["pos_allreduce_peer_dma"].get("checksum_rel_err", 1.0) < 1e-10 and \
-            out["pos_allreduce_peer_dma"]["ms_per_step"] < best["ms_per_step"]:
-        best = out["pos_allreduce_peer_dma"]
-        out["transport"] = "copy engines over peer-mapped buffers (mugiq_b200_comm_attach_peers)"
+    best = out["without_pos_allreduce"]
+    summed = [(k, out[k]) for k in ("pos_allreduce_overlapped", "pos_allreduce_peer_dma")
+              if "ms_per_step" in out.get(k, {}) and out[k].get("checksum_rel_err", 1.0) < 1e-10]
+    if summed:  # the faster of the two overlapped forms whose summed buffer checked out
+        k, best = min(summed, key=lambda kv: kv[1]["ms_per_step"])
+        out["transport"] = ("copy engines over peer-mapped buffers (mugiq_b200_comm_attach_peers)" if k == "pos_allreduce_peer_dma"
+                            else "NCCL all-reduce kernels")
     out["value"] = best["value"]
     out["ms_per_step"] = best["ms_per_step"]
     out["unit"] = UNIT
