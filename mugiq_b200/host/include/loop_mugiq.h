@@ -6,6 +6,8 @@
 #define MUGIQ_B200_LOOP_MUGIQ_H
 #include "displace.h"
 #include "eigsolve_mugiq.h"
+#include <vector>
+
 #include "mugiq.h"
 
 using namespace quda;
@@ -34,6 +36,13 @@ template <typename Float, QudaFieldOrder fieldOrder> class Loop_Mugiq {
   void *momWorkspace_d = nullptr;
   bool fusedMomProj = true;                 // stages 3+4 as one kernel on dataPos_d (no dataPosMP_d)
   void *evecStage_d = nullptr;  // site-major staging for QUDA-native eigenvectors
+  // eigenvector shards, MUGIQ_B200_PEER_REDUCE=1: dataPos_d is an IPC-shareable allocation every rank maps, the overlapped
+  // position-space sum moves its chunks with the copy engines (mugiq_b200_comm_attach_peers) instead of NCCL's kernels
+  bool peerReduce = false;
+  void *peerStage_d = nullptr;
+  char peerPosHandle[64];  // CUDA IPC handle of dataPos_d
+  std::vector<void *> peerOpened;
+  void attachPeerReduce(mugiq_b200_loop_plan_t *plan);
   mugiq_b200_loop_feed_t *feed = nullptr;  // streamed eigenvectors (Eigsolve_Mugiq::setEvecProducer): device staging ring
   int feedBatch = 0;
   void *producerStream = nullptr;          // cudaStream_t the producer enqueues on

@@ -161,9 +161,53 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
     HOST_CUDA(cudaMalloc(&momWorkspace_d, (size_t)ws));
   }
   HOST_CUDA(cudaMallocHost((void **)&dataPos, SizeCplxFloat * nElemPosLoc));  // pinned: the D2H copy of :512 runs at PCIe speed
-  HOST_CUDA(cudaMalloc((void **)&dataPos_d, SizeCplxFloat * nElemPosLoc));
+  const char *pr = getenv("MUGIQ_B200_PEER_REDUCE");
+  peerReduce = pr && atoi(pr) != 0 && getLoopComm() && mugiqCommSize(getLoopComm()) > 1;
+  if (peerReduce) {  // an allocation the other ranks can map (CUDA IPC)
+    void *p = nullptr;
+    MUGIQ_CHECK(mugiq_b200_peer_alloc(&p, (long long)(SizeCplxFloat * nElemPosLoc), peerPosHandle));
+    dataPos_d = static_cast<complex<Float> *>(p);
+  } else {
+    HOST_CUDA(cudaMalloc((void **)&dataPos_d, SizeCplxFloat * nElemPosLoc));
+  }
   HOST_CUDA(cudaMemset(dataPos_d, 0, SizeCplxFloat * nElemPosLoc));
   printfQuda("%s: Data buffers allocated\n", __func__);
+}
+
+// Peer transport of the overlapped position-space sum: the IPC handles of dataPos_d and of a staging area travel through the
+// communicator's all-gather, every peer's pair is mapped and the tables go to the library (once per Loop_Mugiq).
+template <typename Float, QudaFieldOrder fieldOrder>
+void Loop_Mugiq<Float, fieldOrder>::attachPeerReduce(mugiq_b200_loop_plan_t *plan) {
+  MugiqComm *comm = getLoopComm();
+  const int world = mugiqCommSize(comm), rank = mugiqCommRank(comm);
+  const long long stageBytes = mugiq_b200_comm_stage_bytes(plan, 8, world);
+  if (stageBytes < 0) errorQuda("%s: %s", __func__, mugiq_b200_last_error());
+  char mine[128];
+  MUGIQ_CHECK(mugiq_b200_peer_alloc(&peerStage_d, stageBytes, mine + 64));
+  memcpy(mine, peerPosHandle, 64);
+  char *send_d = nullptr, *recv_d = nullptr;
+  std::vector<char> all((size_t)128 * world);
+  HOST_CUDA(cudaMalloc((void **)&send_d, 128));
+  HOST_CUDA(cudaMalloc((void **)&recv_d, (size_t)128 * world));
+  HOST_CUDA(cudaMemcpy(send_d, mine, 128, cudaMemcpyHostToDevice));
+  mugiqCommAllGather(comm, send_d, recv_d, 128);
+  HOST_CUDA(cudaMemcpy(all.data(), recv_d, all.size(), cudaMemcpyDeviceToHost));
+  cudaFree(send_d);
+  cudaFree(recv_d);
+  std::vector<void *> pos(world), stage(world);
+  for (int r = 0; r < world; r++) {
+    if (r == rank) {
+      pos[r] = dataPos_d;
+      stage[r] = peerStage_d;
+      continue;
+    }
+    MUGIQ_CHECK(mugiq_b200_peer_open(&pos[r], all.data() + (size_t)128 * r));
+    MUGIQ_CHECK(mugiq_b200_peer_open(&stage[r], all.data() + (size_t)128 * r + 64));
+    peerOpened.push_back(pos[r]);
+    peerOpened.push_back(stage[r]);
+  }
+  MUGIQ_CHECK(mugiq_b200_comm_attach_peers(mugiqCommHandle(comm), pos.data(), stage.data(), stageBytes));
+  printfQuda("%s: position-space sum over peer-mapped buffers (%d ranks, %.1f MB of staging per rank)\n", __func__, world, stageBytes / 1e6);
 }
 
 template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fieldOrder>::freeDataMemory() {
@@ -180,6 +224,23 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
   hfree(dataMom_bcast);
   if (dataPos) cudaFreeHost(dataPos);
   dataPos = nullptr;
+  if (peerReduce) {  // collective: nobody may still be copying into a buffer that goes away
+    MugiqComm *comm = getLoopComm();
+    cudaDeviceSynchronize();
+    if (!peerOpened.empty()) mugiq_b200_comm_attach_peers(mugiqCommHandle(comm), nullptr, nullptr, 0);
+    auto barrier = [&]() {  // stream-ordered one-element all-reduce, then wait for it
+      mugiqCommStreamBarrier(comm, nullptr);
+      cudaDeviceSynchronize();
+    };
+    barrier();
+    for (void *p : peerOpened) mugiq_b200_peer_close(p);
+    peerOpened.clear();
+    barrier();
+    if (peerStage_d) mugiq_b200_peer_free(peerStage_d);
+    peerStage_d = nullptr;
+    if (dataPos_d) mugiq_b200_peer_free(dataPos_d);
+    dataPos_d = nullptr;
+  }
   dfree(dataPos_d);
   dfree(dataPosMP_d);
   dfree(dataMom_d);
@@ -319,9 +380,11 @@ template <typename Float, QudaFieldOrder fieldOrder> void Loop_Mugiq<Float, fiel
       MUGIQ_CHECK(mugiq_b200_ingest_spinor_batch(stage.data(), src.data(), nb, abi_order(fieldOrder), &geom, nullptr));
     // eigenvector shards (one process per GPU): the last batch's kernels run chunk by chunk in t, each chunk's cross-rank
     // sum over NVLink overlapping the next chunk's kernels (replaces the host-staged MPI collectives, lib/loop_mugiq.cpp:386-424)
-    if (sharded && n0 + nb >= nEv)
+    if (sharded && n0 + nb >= nEv) {
+      if (peerReduce && peerOpened.empty()) attachPeerReduce(plan);
       MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate_allreduce(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0,
                                                             mugiqCommHandle(getLoopComm()), 8, nullptr));
+    }
     else
       MUGIQ_CHECK(mugiq_b200_loop_plan_accumulate(plan, dataPos_d, ptr.data(), sigma.data(), nb, n0 > 0, nullptr));
     printfQuda("%s: Loop trace for eigenvectors %04d - %04d completed\n", __func__, n0, n0 + nb - 1);

@@ -341,6 +341,8 @@ int main(int argc, char **argv) {
     comm = mugiqCommInit(rank, atoi(opt["--comm-size"].c_str()), opt.count("--device") ? atoi(opt["--device"].c_str()) : rank,
                          opt["--comm-id-file"].c_str());
     setLoopComm(comm);
+    // --peer-reduce: the overlapped position-space sum moves its chunks over peer-mapped buffers (copy engines)
+    if (opt.count("--peer-reduce") && yes(opt["--peer-reduce"])) setenv("MUGIQ_B200_PEER_REDUCE", "1", 1);
   } else if (opt.count("--device")) {
     HOST_CUDA(cudaSetDevice(atoi(opt["--device"].c_str())));
   }

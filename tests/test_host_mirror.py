@@ -130,9 +130,11 @@ def test_driver_matches_oracle(driver, oracle, tmp_path, order, prec):
 
 
 @pytest.mark.gpu
-def test_driver_eigenvector_shards_over_nccl(driver, oracle, tmp_path):
-    """Two driver processes, one per GPU, each with its eigenvector shard; the loop buffer is summed with one NCCL
-    all-reduce (comm_mugiq.h).  Every rank ends with the full result."""
+@pytest.mark.parametrize("peer", ["no", "yes"])
+def test_driver_eigenvector_shards_over_nccl(driver, oracle, tmp_path, peer):
+    """Two driver processes, one per GPU, each with its eigenvector shard; the loop buffer is summed chunk by chunk under
+    the kernels, through NCCL or (--peer-reduce yes) by copy-engine pushes over peer-mapped buffers (comm_mugiq.h).
+    Every rank ends with the full result."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (NCCL does not put two ranks on one device)")
@@ -149,11 +151,12 @@ def test_driver_eigenvector_shards_over_nccl(driver, oracle, tmp_path):
                 "--gauge-file", tmp_path / "u.bin", "--loop-do-nonlocal", "yes", "--displace-entry-string", "+z:1,2;-z:1,2;-x:1",
                 "--loop-do-momproj", "yes", "--momenta-filename", tmp_path / "mom.txt", "--comm-size", 2, "--comm-rank", rank,
                 "--comm-id-file", tmp_path / "nccl.id", "--device", rank, "--dump-pos", tmp_path / f"pos{rank}.bin", "--dump-mom",
-                tmp_path / f"mom{rank}.bin"]
+                tmp_path / f"mom{rank}.bin", "--peer-reduce", peer, "--verbosity", "verbose"]
         procs.append(subprocess.Popen([str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     for p in procs:
         out, err = p.communicate(timeout=300)
         assert p.returncode == 0, err
+        assert ("position-space sum over peer-mapped buffers" in out) == (peer == "yes")
     ref = oracle.compute_loop(ev, sig, U, entries, L)
     ref_mom = npc.momentum_projection(ref, mom, -1, L)
     for rank in range(2):
