@@ -14,6 +14,8 @@
 // NCCL launch over the chunk's contiguous runs: per loop, gamma and parity the sites of a time-slice range are
 // V3/2 * nslices consecutive complex numbers) is issued on a high-priority side stream, so that the collective of chunk
 // k travels over NVLink while the FP64-bound kernels of chunk k+1 compute; only the last chunk's sum is exposed.
+// With peers attached (mugiq_b200_comm_attach_peers) the chunks travel by copy-engine pushes over IPC-mapped buffers instead
+// (allreduce_pos_range_peer below): NCCL's all-reduce kernels and the loop kernels want the same SMs, the copy engines do not.
 #include <dlfcn.h>
 #include <nccl.h>
 

@@ -149,6 +149,19 @@ def test_runs_fill_every_lane_on_the_baseline_lattices():
                        bad_maps=0)]
 
 
+def test_ultralocal_matrix_gets_its_own_role_beside_one_to_three_displaced_loops():
+    """The first group carries the ultra-local loop.  With four displaced loops its matrix is shared out among their
+    threads (4 roles x 2 warps); with one to three it has a role of its own, so the CTA's 8 compute warps are
+    (loops + 1) roles x `units` warps - and every site of every role must still be in the stage."""
+    L = (16, 16, 16, 32)
+    for nd, units in ((1, 4), (2, 2), (3, 2), (4, 2)):
+        t0 = tiling(L, [(d, 1, 1, 1) for d in range(nd)])[0]   # plus loops only: nothing is derived, nd computed + UL
+        assert t0["units"] == units and t0["run"] == 16 * units and t0["misses"] == 0 and t0["bad_maps"] == 0, (nd, t0)
+    # a second group never carries the ultra-local loop: 3 displaced loops keep 3 roles x 2 warps there too
+    two_groups = tiling(L, [(d, 1, 1, 1) for d in range(4)] + [(0, 1, 2, 2), (1, 1, 2, 2), (2, 1, 2, 2)])
+    assert len(two_groups) == 2 and all(t["misses"] == 0 and t["bad_maps"] == 0 for t in two_groups)
+
+
 @pytest.mark.parametrize("entries,msg", [([(4, 1, 1, 1)], "direction"), ([(0, 2, 1, 1)], "sign"), ([(0, 1, 3, 1)], "start")])
 def test_bad_entries_are_rejected(entries, msg):
     with pytest.raises(_lib.MugiqB200Error, match=msg):
