@@ -315,18 +315,23 @@ class Loop_Mugiq:
         self._peer = {"stage": stage, "opened": opened}
 
     def close_peer_reduce(self):
-        """Collective: detach and unmap the peer transport (before the buffers are freed)."""
-        if self._peer is None:
+        """Collective, last call on a Loop_Mugiq made with peer_reduce=True: detach and unmap the peer transport, then free
+        the staging area and the shared position-space buffer (dataPos_d is gone afterwards; the host copies stay)."""
+        if not self.peer_reduce:
             return
         import torch.distributed as dist
         torch.cuda.synchronize(self.device)
-        self.comm.attach_peers(None, None, 0)
-        dist.barrier(group=self.group)
-        for ptr in self._peer["opened"]:
-            ops.peer_close(ptr, self.device)
-        dist.barrier(group=self.group)
-        self._peer["stage"].free()
-        self._peer = None
+        if self._peer is not None:
+            self.comm.attach_peers(None, None, 0)
+            dist.barrier(group=self.group)
+            for ptr in self._peer["opened"]:
+                ops.peer_close(ptr, self.device)
+            dist.barrier(group=self.group)
+            self._peer["stage"].free()
+            self._peer = None
+        self.dataPos_d = None
+        self._pos_buf.free()
+        self.peer_reduce = False
 
     def _prepared_batch(self, plan, b0, b1, vecs):
         """Argument tables (pointer array, sigma array) of the resident batch [b0, b1): built once and reused while the
